@@ -57,6 +57,7 @@ class _Matrix:
 
 
 _installed = False
+_mods = None
 qp_log = []          # every solvers.qp call: dict(P,q,G,h,A,b,result)
 qp_log_enabled = False
 
@@ -99,15 +100,31 @@ def install():
 
 def modules():
     """Return (path_planning, planning_utils, speed_planning_test) of the reference."""
+    global _mods
+    if _mods is not None:
+        return _mods
     install()
     import warnings
     warnings.filterwarnings("ignore", category=DeprecationWarning)
     # the repo ships its own drop-in `planner` package; make sure the reference's wins here
-    for name in [k for k in sys.modules if k == "planner" or k.startswith("planner.")]:
-        mod = sys.modules[name]
-        if not getattr(mod, "__file__", "").startswith(REFERENCE_ROOT):
-            del sys.modules[name]
-    sys.path.remove(REFERENCE_ROOT)
+    def _is_ref(mod):
+        f = getattr(mod, "__file__", None)
+        if f:
+            return f.startswith(REFERENCE_ROOT)
+        return any(str(p).startswith(REFERENCE_ROOT) for p in getattr(mod, "__path__", []))
+    saved = {k: sys.modules.pop(k) for k in list(sys.modules)
+             if (k == "planner" or k.startswith("planner.")) and not _is_ref(sys.modules[k])}
+    if REFERENCE_ROOT in sys.path:
+        sys.path.remove(REFERENCE_ROOT)
     sys.path.insert(0, REFERENCE_ROOT)
-    from planner import path_planning, planning_utils, speed_planning_test
-    return path_planning, planning_utils, speed_planning_test
+    try:
+        from planner import path_planning, planning_utils, speed_planning_test
+        mods = (path_planning, planning_utils, speed_planning_test)
+    finally:
+        # leave sys.modules as found for the repo's own drop-in package
+        for k in [k for k in sys.modules if k == "planner" or k.startswith("planner.")]:
+            del sys.modules[k]
+        sys.modules.update(saved)
+        sys.path.remove(REFERENCE_ROOT)
+    _mods = mods
+    return mods
