@@ -1,0 +1,111 @@
+"""ctypes binding of libemplanner.so (include/emplanner.h).  No fallback: if the
+CUDA library is missing or a call fails, an exception is raised."""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libemplanner.so")
+
+
+class EmpError(RuntimeError):
+    pass
+
+
+class DpParams(C.Structure):
+    """EmpDpParams: DP_algorithm keyword defaults (reference path_planning.py:276-279)."""
+    _fields_ = [("sampling_res", C.c_double), ("w_collision", C.c_double), ("w_smooth", C.c_double * 3),
+                ("w_ref", C.c_double), ("sample_s", C.c_double), ("sample_l", C.c_double),
+                ("row", C.c_int32), ("col", C.c_int32)]
+
+
+class QpParams(C.Structure):
+    """EmpQpParams: Quadratic_planning / cal_lmin_lmax / cvxopt defaults (path_planning.py:78-81,222)."""
+    _fields_ = [("dp_sampling_res", C.c_double), ("w_l", C.c_double), ("w_dl", C.c_double), ("w_ddl", C.c_double),
+                ("w_dddl", C.c_double), ("w_centre", C.c_double), ("w_end_l", C.c_double), ("w_end_dl", C.c_double),
+                ("w_end_ddl", C.c_double), ("host_d1", C.c_double), ("host_d2", C.c_double), ("host_w", C.c_double),
+                ("obs_length", C.c_double), ("obs_width", C.c_double), ("abstol", C.c_double), ("reltol", C.c_double),
+                ("feastol", C.c_double), ("maxiters", C.c_int32), ("reserved", C.c_int32)]
+
+
+_P = C.c_void_p
+_DPP = C.POINTER(DpParams)
+_QPP = C.POINTER(QpParams)
+_SIGNATURES = {
+    "emp_dp_params_default": (None, [_DPP]),
+    "emp_qp_params_default": (None, [_QPP]),
+    "emp_scene_stride": (C.c_int, [C.c_int]),
+    "emp_plan_stride": (C.c_int, [C.c_int]),
+    "emp_max_enriched": (C.c_int, [_DPP]),
+    "emp_version": (C.c_int, []),
+    "emp_last_error": (C.c_char_p, []),
+    "emp_sl_dp_dev": (C.c_int, [_P, C.c_int, C.c_int, _DPP, C.c_int, _P, _P, _P]),
+    "emp_sl_qp_dev": (C.c_int, [_P, C.c_int, C.c_int, _QPP, C.c_int, _P, _P, _P]),
+    "emp_qp_dev": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, _QPP, _P, _P, _P]),
+    "emp_corridor_dev": (C.c_int, [_P, _P, C.c_int, _P, C.c_int, C.c_int, _QPP, _P, _P, _P]),
+    "emp_sl_plan_dev": (C.c_int, [_P, C.c_int, C.c_int, _DPP, _QPP, C.c_int, _P, _P, _P]),
+    "emp_fp64_peak": (C.c_int, [C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
+    "emp_planner_create": (C.c_int, [C.POINTER(_P), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),
+    "emp_planner_destroy": (None, [_P]),
+    "emp_sl_plan_host": (C.c_int, [_P, _P, C.c_int, _DPP, _QPP, _P, _P]),
+    "emp_sl_dp_host": (C.c_int, [_P, _P, C.c_int, _DPP, _P, _P]),
+    "emp_qp_host": (C.c_int, [_P, _P, _P, _P, C.c_int, C.c_int, _QPP, _P, _P]),
+    "emp_corridor_host": (C.c_int, [_P, _P, _P, C.c_int, _P, C.c_int, _QPP, _P, _P]),
+    "emp_planner_last_kernel_ms": (C.c_double, [_P]),
+}
+
+_lib = None
+
+
+def exported_symbols():
+    """Names include/emplanner.h declares (a CPU test checks the .so exports every one of them)."""
+    return sorted(_SIGNATURES)
+
+
+def lib():
+    """Load the shared library once.  Loading does NOT touch CUDA (fork-safe, reference test_9.py:226-227)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise EmpError("libemplanner.so not built (%s). Run `python -c 'import __graft_entry__ as g; g.build()'` "
+                           "or `python emplanner_carla_b200/csrc/build.py`. There is no CPU fallback." % LIB_PATH)
+        handle = C.CDLL(LIB_PATH)
+        for name, (res, args) in _SIGNATURES.items():
+            fn = getattr(handle, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = handle
+    return _lib
+
+
+def check(rc):
+    if rc != 0:
+        raise EmpError("libemplanner error %d: %s" % (rc, lib().emp_last_error().decode()))
+
+
+def dp_params(sampling_res=2, w_collision_cost=1e12, w_smooth_cost=(300, 1000, 5000), w_reference_cost=20,
+              row=12, col=6, sample_s=15, sample_l=1.5):
+    p = DpParams()
+    p.sampling_res = float(sampling_res)
+    p.w_collision = float(w_collision_cost)
+    p.w_smooth = (C.c_double * 3)(*[float(v) for v in w_smooth_cost])
+    p.w_ref = float(w_reference_cost)
+    p.sample_s = float(sample_s)
+    p.sample_l = float(sample_l)
+    p.row = int(row)
+    p.col = int(col)
+    return p
+
+
+def qp_params(dp_sampling_res=2, w_cost_l=1000, w_cost_dl=10000, w_cost_ddl=3000, w_cost_dddl=150,
+              w_cost_centre=250, w_cost_end_l=40, w_cost_end_dl=40, w_cost_end_ddl=40, host_d1=3, host_d2=3,
+              host_w=3, obs_length=5, obs_width=5, abstol=1e-7, reltol=1e-6, feastol=1e-7, maxiters=100):
+    p = QpParams()
+    p.dp_sampling_res = float(dp_sampling_res)
+    p.w_l, p.w_dl, p.w_ddl, p.w_dddl = float(w_cost_l), float(w_cost_dl), float(w_cost_ddl), float(w_cost_dddl)
+    p.w_centre = float(w_cost_centre)
+    p.w_end_l, p.w_end_dl, p.w_end_ddl = float(w_cost_end_l), float(w_cost_end_dl), float(w_cost_end_ddl)
+    p.host_d1, p.host_d2, p.host_w = float(host_d1), float(host_d2), float(host_w)
+    p.obs_length, p.obs_width = float(obs_length), float(obs_width)
+    p.abstol, p.reltol, p.feastol = float(abstol), float(reltol), float(feastol)
+    p.maxiters = int(maxiters)
+    return p

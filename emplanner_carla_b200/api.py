@@ -1,0 +1,224 @@
+"""Batched S-L planning API on top of the C ABI (include/emplanner.h).
+
+Two ways in:
+  * HostPlanner  - numpy host buffers in/out through the `*_host` entry points
+                   (the library owns streams and device workspace; no torch needed).
+                   This is what the drop-in `planner/` modules use, and the
+                   end-to-end (`e2e`) benchmark path.
+  * plan_device  - torch CUDA tensors as device-memory containers through the
+                   `*_dev` entry points on torch's current stream.
+There is no CPU fallback anywhere: every call ends in libemplanner.so.
+"""
+import ctypes as C
+import numpy as np
+
+from . import _lib
+from ._lib import EmpError, dp_params, qp_params  # noqa: F401  (re-exported)
+
+PLAN_HDR = 8
+SCENE_HDR = 6
+
+DP_NO_OBSTACLE, DP_ALL_COLLIDE, DP_OVERFLOW = 1, 2, 4
+QP_OK, QP_UNKNOWN_MAXITER, QP_UNKNOWN_NUMERIC, QP_CORRIDOR_INDEX, QP_TOO_LARGE = 0, 1, 2, 4, 8
+
+
+def scene_stride(kmax=8):
+    return SCENE_HDR + 2 * int(kmax)
+
+
+def plan_stride(n_enr_max):
+    return _lib.lib().emp_plan_stride(int(n_enr_max))
+
+
+def max_enriched(dp):
+    return _lib.lib().emp_max_enriched(C.byref(dp))
+
+
+def pack_scenes(obs_s, obs_l, nobs, s0, l0, dl0, ddl0, kmax=8):
+    """Build the [B, 6+2*kmax] float64 scene records (layout: include/emplanner.h)."""
+    s0 = np.atleast_1d(np.asarray(s0, dtype=np.float64))
+    B = s0.shape[0]
+    if kmax % 2 or kmax > 32:
+        raise ValueError("kmax must be even and <= 32")
+    rec = np.zeros((B, scene_stride(kmax)), dtype=np.float64)
+    rec[:, 0] = s0
+    rec[:, 1] = np.asarray(l0, dtype=np.float64)
+    rec[:, 2] = np.asarray(dl0, dtype=np.float64)
+    rec[:, 3] = np.asarray(ddl0, dtype=np.float64)
+    rec[:, 4] = np.asarray(nobs, dtype=np.float64)
+    obs_s = np.asarray(obs_s, dtype=np.float64).reshape(B, -1)
+    obs_l = np.asarray(obs_l, dtype=np.float64).reshape(B, -1)
+    k_in = obs_s.shape[1]
+    if k_in > kmax:
+        raise ValueError("more obstacle slots (%d) than kmax (%d)" % (k_in, kmax))
+    rec[:, SCENE_HDR:SCENE_HDR + k_in] = np.nan_to_num(obs_s, nan=0.0)
+    rec[:, SCENE_HDR + kmax:SCENE_HDR + kmax + k_in] = np.nan_to_num(obs_l, nan=0.0)
+    return rec
+
+
+class PlanView:
+    """Field views over a [B, plan_stride] float64 plan-record array (numpy or torch)."""
+
+    def __init__(self, plans, n_enr_max):
+        self.raw = plans
+        self.NE = int(n_enr_max)
+        self.NQ = (self.NE + 1) // 2
+
+    def _col(self, k):
+        return self.raw[:, k]
+
+    n_enr = property(lambda self: self._col(0))
+    n_qp = property(lambda self: self._col(1))
+    dp_status = property(lambda self: self._col(2))
+    qp_status = property(lambda self: self._col(3))
+    qp_iters = property(lambda self: self._col(4))
+    dp_cost = property(lambda self: self._col(5))
+    gap = property(lambda self: self._col(6))
+
+    @property
+    def enr_s(self):
+        return self.raw[:, PLAN_HDR:PLAN_HDR + self.NE]
+
+    @property
+    def enr_l(self):
+        return self.raw[:, PLAN_HDR + self.NE:PLAN_HDR + 2 * self.NE]
+
+    def _qp(self, k):
+        o = PLAN_HDR + 2 * self.NE + k * self.NQ
+        return self.raw[:, o:o + self.NQ]
+
+    qp_l = property(lambda self: self._qp(0))
+    qp_dl = property(lambda self: self._qp(1))
+    qp_ddl = property(lambda self: self._qp(2))
+
+
+def _ptr(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+class HostPlanner:
+    """EmpPlanner handle: host buffers in, host buffers out.  CUDA is first touched here,
+    never at import (the reference forks its planner process before planning, test_9.py:226-227)."""
+
+    def __init__(self, max_batch, kmax=8, n_enr_max=64, max_col=64, device=-1):
+        self._h = C.c_void_p()
+        self.max_batch, self.kmax, self.n_enr_max, self.max_col = int(max_batch), int(kmax), int(n_enr_max), int(max_col)
+        _lib.check(_lib.lib().emp_planner_create(C.byref(self._h), int(device), self.max_batch, self.kmax,
+                                                 self.n_enr_max, self.max_col))
+
+    def close(self):
+        if self._h:
+            _lib.lib().emp_planner_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check_scenes(self, scenes):
+        scenes = np.ascontiguousarray(scenes, dtype=np.float64)
+        if scenes.ndim != 2 or scenes.shape[1] != scene_stride(self.kmax):
+            raise ValueError("scenes must be [B, %d]" % scene_stride(self.kmax))
+        return scenes
+
+    def plan(self, scenes, dp, qp, want_rows=False, out=None):
+        """DP -> [::2] -> corridor -> QP for a batch.  Returns (PlanView, rows or None)."""
+        scenes = self._check_scenes(scenes)
+        B = scenes.shape[0]
+        plans = out if out is not None else np.empty((B, plan_stride(self.n_enr_max)), dtype=np.float64)
+        rows = np.empty((B, dp.col), dtype=np.int32) if want_rows else None
+        _lib.check(_lib.lib().emp_sl_plan_host(self._h, _ptr(scenes), B, C.byref(dp), C.byref(qp), _ptr(plans),
+                                               _ptr(rows) if want_rows else None))
+        return PlanView(plans, self.n_enr_max), rows
+
+    def dp(self, scenes, dp, want_rows=True):
+        """DP_algorithm for a batch (no QP)."""
+        scenes = self._check_scenes(scenes)
+        B = scenes.shape[0]
+        plans = np.zeros((B, plan_stride(self.n_enr_max)), dtype=np.float64)
+        rows = np.empty((B, dp.col), dtype=np.int32) if want_rows else None
+        _lib.check(_lib.lib().emp_sl_dp_host(self._h, _ptr(scenes), B, C.byref(dp), _ptr(plans),
+                                             _ptr(rows) if want_rows else None))
+        return PlanView(plans, self.n_enr_max), rows
+
+    def qp(self, l_min, l_max, start, qp):
+        """Quadratic_planning for a batch of corridors [B, n].  Returns (x [B,3,n], status [B], iters [B])."""
+        l_min = np.ascontiguousarray(l_min, dtype=np.float64)
+        l_max = np.ascontiguousarray(l_max, dtype=np.float64)
+        start = np.ascontiguousarray(start, dtype=np.float64)
+        B, n = l_min.shape
+        out = np.zeros((B, 3, n), dtype=np.float64)
+        si = np.zeros((B, 2), dtype=np.int32)
+        _lib.check(_lib.lib().emp_qp_host(self._h, _ptr(l_min), _ptr(l_max), _ptr(start), n, B, C.byref(qp),
+                                          _ptr(out), _ptr(si)))
+        return out, si[:, 0].copy(), si[:, 1].copy()
+
+    def corridor(self, dp_s, dp_l, scenes, qp):
+        """cal_lmin_lmax for a batch of paths [B, n].  Returns (lmin [B,n], lmax [B,n], status [B])."""
+        dp_s = np.ascontiguousarray(dp_s, dtype=np.float64)
+        dp_l = np.ascontiguousarray(dp_l, dtype=np.float64)
+        scenes = self._check_scenes(scenes)
+        B, n = dp_s.shape
+        out = np.zeros((B, 2, n), dtype=np.float64)
+        si = np.zeros((B, 2), dtype=np.int32)
+        _lib.check(_lib.lib().emp_corridor_host(self._h, _ptr(dp_s), _ptr(dp_l), n, _ptr(scenes), B, C.byref(qp),
+                                                _ptr(out), _ptr(si)))
+        return out[:, 0].copy(), out[:, 1].copy(), si[:, 0].copy()
+
+    @property
+    def last_kernel_ms(self):
+        return _lib.lib().emp_planner_last_kernel_ms(self._h)
+
+
+# ---- device-tensor path (torch tensors as device-memory containers) ---------------
+
+def _dev_ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def _stream_ptr():
+    import torch
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def plan_device(scenes, dp, qp, n_enr_max, plans=None, rows=None, kmax=None):
+    """S-L planning step on device tensors: scenes [B, 6+2*kmax] f64 cuda -> plans [B, stride] f64 cuda.
+    Enqueues two kernels on torch's current stream and returns immediately."""
+    import torch
+    if not scenes.is_cuda or scenes.dtype != torch.float64 or not scenes.is_contiguous():
+        raise ValueError("scenes must be a contiguous float64 CUDA tensor")
+    B = scenes.shape[0]
+    kmax = (scenes.shape[1] - SCENE_HDR) // 2 if kmax is None else kmax
+    if plans is None:
+        plans = torch.empty((B, plan_stride(n_enr_max)), dtype=torch.float64, device=scenes.device)
+    _lib.check(_lib.lib().emp_sl_plan_dev(_dev_ptr(scenes), kmax, B, C.byref(dp), C.byref(qp), int(n_enr_max),
+                                          _dev_ptr(plans), _dev_ptr(rows), _stream_ptr()))
+    return plans
+
+
+def dp_device(scenes, dp, n_enr_max, plans=None, rows=None):
+    import torch
+    B = scenes.shape[0]
+    kmax = (scenes.shape[1] - SCENE_HDR) // 2
+    if plans is None:
+        plans = torch.zeros((B, plan_stride(n_enr_max)), dtype=torch.float64, device=scenes.device)
+    _lib.check(_lib.lib().emp_sl_dp_dev(_dev_ptr(scenes), kmax, B, C.byref(dp), int(n_enr_max), _dev_ptr(plans),
+                                        _dev_ptr(rows), _stream_ptr()))
+    return plans
+
+
+def qp_device(scenes, qp, n_enr_max, plans, lmin_lmax=None):
+    B = scenes.shape[0]
+    kmax = (scenes.shape[1] - SCENE_HDR) // 2
+    _lib.check(_lib.lib().emp_sl_qp_dev(_dev_ptr(scenes), kmax, B, C.byref(qp), int(n_enr_max), _dev_ptr(plans),
+                                        _dev_ptr(lmin_lmax), _stream_ptr()))
+    return plans
+
+
+def fp64_peak(iters=4096):
+    """Measured FP64 FMA throughput of the current device (TFLOP/s, ms)."""
+    t, ms = C.c_double(), C.c_double()
+    _lib.check(_lib.lib().emp_fp64_peak(int(iters), C.byref(t), C.byref(ms)))
+    return t.value, ms.value

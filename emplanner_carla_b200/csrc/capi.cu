@@ -1,0 +1,335 @@
+// C ABI of libemplanner.so (see include/emplanner.h).  Host-side glue only:
+// argument checking, shared-memory carve-up, launches, the host-buffer planner
+// handle, and the FP64 FMA micro-benchmark used as roofline denominator.
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include "emp_common.cuh"
+#include "sl_kernels.h"
+
+namespace {
+
+thread_local char g_err[512] = "";
+
+int fail(int code, const char *fmt, const char *detail = "") {
+    snprintf(g_err, sizeof(g_err), fmt, detail);
+    return code;
+}
+int fail_cuda(cudaError_t e, const char *where) {
+    snprintf(g_err, sizeof(g_err), "%s: %s", where, cudaGetErrorString(e));
+    return -100 - (int)e;
+}
+
+inline int align_up(int v, int a) { return (v + a - 1) / a * a; }
+
+int make_dp_launch(emp::DpLaunch &L, const EmpDpParams *p, int kmax, int batch, int n_enr_max) {
+    if (!p) return fail(-1, "EmpDpParams is NULL");
+    if (p->row < 1 || p->row > EMP_MAX_ROW) return fail(-2, "row must be in [1, 16]");
+    if (p->col < 1 || p->col > 4096) return fail(-2, "col must be in [1, 4096]");
+    if (kmax < 0 || kmax > EMP_MAX_KMAX || (kmax & 1)) return fail(-2, "kmax must be even and in [0, 32]");
+    if (!(p->sample_s > 0) || !(p->sampling_res > 0)) return fail(-2, "sample_s and sampling_res must be > 0");
+    if (batch < 0 || n_enr_max < 2) return fail(-2, "bad batch / n_enr_max");
+    L.res = p->sampling_res;
+    L.w_col = p->w_collision;
+    L.w0 = p->w_smooth[0];
+    L.w1 = p->w_smooth[1];
+    L.w2 = p->w_smooth[2];
+    L.w_ref = p->w_ref;
+    L.sample_s = p->sample_s;
+    L.sample_l = p->sample_l;
+    L.R = p->row;
+    L.C = p->col;
+    L.kmax = kmax;
+    L.n_enr_max = n_enr_max;
+    L.scene_stride = emp_scene_stride(kmax);
+    L.plan_stride = emp_plan_stride(n_enr_max);
+    L.batch = batch;
+    const int RR = L.R * L.R;
+    int off = 16;                                        // mbarrier
+    L.off_slab = off;  off += align_up(emp::DP_WARPS * L.scene_stride * 8, 16);
+    L.off_f0 = off;    off += align_up(EMP_NSAMPLE * 8, 16);
+    L.off_nl = off;    off += EMP_MAX_ROW * 8;
+    L.off_refc = off;  off += align_up(RR * 8, 16);
+    L.off_warp = off;
+    int w = 0;
+    L.w_off_cand = w;   w += align_up(RR * 8, 16);
+    L.w_off_cost = w;   w += 2 * EMP_MAX_ROW * 8;
+    L.w_off_rows = w;   w += align_up(L.C * 4, 16);
+    L.w_off_offs = w;   w += align_up((L.C + 1) * 4, 16);
+    L.w_off_parent = w; w += align_up(L.C * L.R, 16);
+    L.warp_bytes = w;
+    L.smem_bytes = (unsigned)(off + emp::DP_WARPS * w);
+    if (L.smem_bytes > 227u * 1024u) return fail(-3, "lattice too large for shared memory (row*col)");
+    return 0;
+}
+
+int make_qp_launch(emp::QpLaunch &L, const EmpQpParams *p, int kmax, int batch, int n_enr_max, int n_direct, int mode) {
+    if (!p) return fail(-1, "EmpQpParams is NULL");
+    if (!(p->dp_sampling_res > 0)) return fail(-2, "dp_sampling_res must be > 0");
+    if (kmax < 0 || kmax > EMP_MAX_KMAX || (kmax & 1)) return fail(-2, "kmax must be even and in [0, 32]");
+    L.q = *p;
+    L.batch = batch;
+    L.kmax = kmax;
+    L.scene_stride = emp_scene_stride(kmax);
+    L.plan_stride = emp_plan_stride(n_enr_max);
+    L.n_enr_max = n_enr_max;
+    L.n_direct = n_direct;
+    L.mode = mode;
+    return 0;
+}
+
+}  // namespace
+
+struct EmpPlanner {
+    int device = 0, max_batch = 0, kmax = 0, n_enr_max = 0, max_col = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    double *d_scenes = nullptr, *d_plans = nullptr, *d_qp_in = nullptr, *d_qp_out = nullptr;
+    int32_t *d_rows = nullptr, *d_status = nullptr;
+    double *h_scenes = nullptr, *h_plans = nullptr;       // pinned staging
+    int32_t *h_rows = nullptr;
+    float last_ms = 0.f;
+};
+
+extern "C" {
+
+void emp_dp_params_default(EmpDpParams *p) {
+    p->sampling_res = 2; p->w_collision = 1e12;
+    p->w_smooth[0] = 300; p->w_smooth[1] = 1000; p->w_smooth[2] = 5000;
+    p->w_ref = 20; p->sample_s = 15; p->sample_l = 1.5; p->row = 12; p->col = 6;
+}
+
+void emp_qp_params_default(EmpQpParams *p) {
+    p->dp_sampling_res = 2;
+    p->w_l = 1000; p->w_dl = 10000; p->w_ddl = 3000; p->w_dddl = 150; p->w_centre = 250;
+    p->w_end_l = 40; p->w_end_dl = 40; p->w_end_ddl = 40;
+    p->host_d1 = 3; p->host_d2 = 3; p->host_w = 3;
+    p->obs_length = 5; p->obs_width = 5;
+    p->abstol = 1e-7; p->reltol = 1e-6; p->feastol = 1e-7;
+    p->maxiters = 100; p->reserved = 0;
+}
+
+int emp_scene_stride(int kmax) { return EMP_SCENE_HDR + 2 * kmax; }
+
+int emp_plan_stride(int n_enr_max) {
+    const int nq = (n_enr_max + 1) / 2;
+    return (EMP_PLAN_HDR + 2 * n_enr_max + 3 * nq + 1) & ~1;
+}
+
+int emp_max_enriched(const EmpDpParams *p) {
+    const int per = (int)std::floor(p->sample_s / p->sampling_res) + 1;
+    return p->col * per + 1;
+}
+
+int emp_version(void) { return EMP_VERSION; }
+const char *emp_last_error(void) { return g_err; }
+
+int emp_sl_dp_dev(const double *scenes, int kmax, int batch, const EmpDpParams *p, int n_enr_max,
+                  double *plans, int32_t *rows, void *stream) {
+    emp::DpLaunch L;
+    if (int rc = make_dp_launch(L, p, kmax, batch, n_enr_max)) return rc;
+    if (batch == 0) return 0;
+    if (!scenes || !plans) return fail(-1, "scenes/plans is NULL");
+    cudaError_t e = emp::launch_sl_dp(scenes, plans, rows, L, (cudaStream_t)stream);
+    return e == cudaSuccess ? 0 : fail_cuda(e, "sl_dp launch");
+}
+
+int emp_sl_qp_dev(const double *scenes, int kmax, int batch, const EmpQpParams *p, int n_enr_max,
+                  double *plans, double *lmin_lmax, void *stream) {
+    emp::QpLaunch L;
+    if (int rc = make_qp_launch(L, p, kmax, batch, n_enr_max, 0, emp::QP_MODE_FUSED)) return rc;
+    if (batch == 0) return 0;
+    if (!scenes || !plans) return fail(-1, "scenes/plans is NULL");
+    cudaError_t e = emp::launch_sl_qp(scenes, plans, lmin_lmax, nullptr, nullptr, nullptr, nullptr, nullptr, L,
+                                      (cudaStream_t)stream);
+    return e == cudaSuccess ? 0 : fail_cuda(e, "sl_qp launch");
+}
+
+int emp_qp_dev(const double *l_min, const double *l_max, const double *start, int n, int batch,
+               const EmpQpParams *p, double *out, int32_t *status_iters, void *stream) {
+    emp::QpLaunch L;
+    if (n < 1) return fail(-2, "n must be >= 1");
+    if (int rc = make_qp_launch(L, p, 0, batch, 2, n, emp::QP_MODE_DIRECT)) return rc;
+    if (batch == 0) return 0;
+    if (!l_min || !l_max || !start || !out || !status_iters) return fail(-1, "NULL argument");
+    cudaError_t e = emp::launch_sl_qp(nullptr, nullptr, nullptr, l_min, l_max, start, out, status_iters, L,
+                                      (cudaStream_t)stream);
+    return e == cudaSuccess ? 0 : fail_cuda(e, "qp launch");
+}
+
+int emp_corridor_dev(const double *dp_s, const double *dp_l, int n, const double *scenes, int kmax, int batch,
+                     const EmpQpParams *p, double *lmin_lmax, int32_t *status_iters, void *stream) {
+    emp::QpLaunch L;
+    if (n < 1) return fail(-2, "n must be >= 1");
+    if (int rc = make_qp_launch(L, p, kmax, batch, 2, n, emp::QP_MODE_CORRIDOR)) return rc;
+    if (batch == 0) return 0;
+    if (!dp_s || !dp_l || !scenes || !lmin_lmax || !status_iters) return fail(-1, "NULL argument");
+    cudaError_t e = emp::launch_sl_qp(scenes, nullptr, lmin_lmax, dp_s, dp_l, nullptr, nullptr, status_iters, L,
+                                      (cudaStream_t)stream);
+    return e == cudaSuccess ? 0 : fail_cuda(e, "corridor launch");
+}
+
+int emp_sl_plan_dev(const double *scenes, int kmax, int batch, const EmpDpParams *dp, const EmpQpParams *qp,
+                    int n_enr_max, double *plans, int32_t *rows, void *stream) {
+    if (int rc = emp_sl_dp_dev(scenes, kmax, batch, dp, n_enr_max, plans, rows, stream)) return rc;
+    return emp_sl_qp_dev(scenes, kmax, batch, qp, n_enr_max, plans, nullptr, stream);
+}
+
+int emp_fp64_peak(int iters, double *tflops, double *ms) {
+    cudaError_t e = emp::launch_fp64_peak(iters, tflops, ms);
+    return e == cudaSuccess ? 0 : fail_cuda(e, "fp64 peak");
+}
+
+// ---- host-buffer planner --------------------------------------------------------
+#define EMP_CK(call, what)                                   \
+    do {                                                     \
+        cudaError_t e_ = (call);                             \
+        if (e_ != cudaSuccess) return fail_cuda(e_, what);   \
+    } while (0)
+
+int emp_planner_create(EmpPlanner **out, int device, int max_batch, int kmax, int n_enr_max, int max_col) {
+    if (!out) return fail(-1, "out is NULL");
+    *out = nullptr;
+    if (max_batch < 1 || n_enr_max < 2 || max_col < 1) return fail(-2, "bad planner sizes");
+    if (kmax < 0 || kmax > EMP_MAX_KMAX || (kmax & 1)) return fail(-2, "kmax must be even and in [0, 32]");
+    if (device < 0) EMP_CK(cudaGetDevice(&device), "cudaGetDevice");
+    EMP_CK(cudaSetDevice(device), "cudaSetDevice");
+    EmpPlanner *pl = new (std::nothrow) EmpPlanner();
+    if (!pl) return fail(-4, "out of host memory");
+    pl->device = device; pl->max_batch = max_batch; pl->kmax = kmax; pl->n_enr_max = n_enr_max; pl->max_col = max_col;
+    const size_t sb = (size_t)max_batch * emp_scene_stride(kmax) * 8;
+    const size_t pb = (size_t)max_batch * emp_plan_stride(n_enr_max) * 8;
+    const size_t rb = (size_t)max_batch * max_col * 4;
+    const size_t qb = (size_t)max_batch * 3 * EMP_MAX_QP_POINTS * 8;
+    cudaError_t e = cudaSuccess;
+    auto ok = [&](cudaError_t r) { if (e == cudaSuccess) e = r; };
+    ok(cudaStreamCreateWithFlags(&pl->stream, cudaStreamNonBlocking));
+    ok(cudaEventCreate(&pl->ev0));
+    ok(cudaEventCreate(&pl->ev1));
+    ok(cudaMalloc(&pl->d_scenes, sb));
+    ok(cudaMalloc(&pl->d_plans, pb));
+    ok(cudaMalloc(&pl->d_rows, rb));
+    ok(cudaMalloc(&pl->d_qp_in, qb));
+    ok(cudaMalloc(&pl->d_qp_out, qb));
+    ok(cudaMalloc(&pl->d_status, (size_t)max_batch * 2 * 4));
+    ok(cudaMallocHost(&pl->h_scenes, sb));
+    ok(cudaMallocHost(&pl->h_plans, pb));
+    ok(cudaMallocHost(&pl->h_rows, rb));
+    if (e != cudaSuccess) {
+        emp_planner_destroy(pl);
+        return fail_cuda(e, "planner allocation");
+    }
+    *out = pl;
+    return 0;
+}
+
+void emp_planner_destroy(EmpPlanner *pl) {
+    if (!pl) return;
+    cudaSetDevice(pl->device);
+    if (pl->stream) cudaStreamSynchronize(pl->stream);
+    cudaFree(pl->d_scenes); cudaFree(pl->d_plans); cudaFree(pl->d_rows);
+    cudaFree(pl->d_qp_in); cudaFree(pl->d_qp_out); cudaFree(pl->d_status);
+    cudaFreeHost(pl->h_scenes); cudaFreeHost(pl->h_plans); cudaFreeHost(pl->h_rows);
+    if (pl->ev0) cudaEventDestroy(pl->ev0);
+    if (pl->ev1) cudaEventDestroy(pl->ev1);
+    if (pl->stream) cudaStreamDestroy(pl->stream);
+    delete pl;
+}
+
+static int plan_host_impl(EmpPlanner *pl, const double *scenes, int batch, const EmpDpParams *dp,
+                          const EmpQpParams *qp, double *plans, int32_t *rows) {
+    if (!pl || !scenes || !plans || !dp) return fail(-1, "NULL argument");
+    if (batch < 0 || batch > pl->max_batch) return fail(-2, "batch exceeds planner capacity");
+    if (dp->col > pl->max_col) return fail(-2, "col exceeds planner capacity");
+    if (emp_max_enriched(dp) > pl->n_enr_max) return fail(-2, "lattice needs a larger n_enr_max than the planner was created with");
+    if (batch == 0) return 0;
+    EMP_CK(cudaSetDevice(pl->device), "cudaSetDevice");
+    const size_t sb = (size_t)batch * emp_scene_stride(pl->kmax) * 8;
+    const size_t pb = (size_t)batch * emp_plan_stride(pl->n_enr_max) * 8;
+    const size_t rb = (size_t)batch * dp->col * 4;
+    // Caller buffers may be pageable: stage through pinned memory so the copies are truly asynchronous DMA.
+    memcpy(pl->h_scenes, scenes, sb);
+    EMP_CK(cudaMemcpyAsync(pl->d_scenes, pl->h_scenes, sb, cudaMemcpyHostToDevice, pl->stream), "H2D scenes");
+    EMP_CK(cudaEventRecord(pl->ev0, pl->stream), "event");
+    int rc = emp_sl_dp_dev(pl->d_scenes, pl->kmax, batch, dp, pl->n_enr_max, pl->d_plans, rows ? pl->d_rows : nullptr, pl->stream);
+    if (rc) return rc;
+    if (qp) {
+        rc = emp_sl_qp_dev(pl->d_scenes, pl->kmax, batch, qp, pl->n_enr_max, pl->d_plans, nullptr, pl->stream);
+        if (rc) return rc;
+    }
+    EMP_CK(cudaEventRecord(pl->ev1, pl->stream), "event");
+    EMP_CK(cudaMemcpyAsync(pl->h_plans, pl->d_plans, pb, cudaMemcpyDeviceToHost, pl->stream), "D2H plans");
+    if (rows) EMP_CK(cudaMemcpyAsync(pl->h_rows, pl->d_rows, rb, cudaMemcpyDeviceToHost, pl->stream), "D2H rows");
+    EMP_CK(cudaStreamSynchronize(pl->stream), "planner stream");
+    memcpy(plans, pl->h_plans, pb);
+    if (rows) memcpy(rows, pl->h_rows, rb);
+    cudaEventElapsedTime(&pl->last_ms, pl->ev0, pl->ev1);
+    return 0;
+}
+
+int emp_sl_plan_host(EmpPlanner *pl, const double *scenes, int batch, const EmpDpParams *dp,
+                     const EmpQpParams *qp, double *plans, int32_t *rows) {
+    if (!qp) return fail(-1, "EmpQpParams is NULL");
+    return plan_host_impl(pl, scenes, batch, dp, qp, plans, rows);
+}
+
+int emp_sl_dp_host(EmpPlanner *pl, const double *scenes, int batch, const EmpDpParams *dp, double *plans,
+                   int32_t *rows) {
+    return plan_host_impl(pl, scenes, batch, dp, nullptr, plans, rows);
+}
+
+int emp_qp_host(EmpPlanner *pl, const double *l_min, const double *l_max, const double *start, int n, int batch,
+                const EmpQpParams *p, double *out, int32_t *status_iters) {
+    if (!pl || !l_min || !l_max || !start || !out || !status_iters) return fail(-1, "NULL argument");
+    if (batch < 0 || batch > pl->max_batch) return fail(-2, "batch exceeds planner capacity");
+    if (n < 1 || n > EMP_MAX_QP_POINTS) {
+        // report like the kernel would, without launching
+        for (int b = 0; b < batch; ++b) { status_iters[2 * b] = EMP_QP_TOO_LARGE; status_iters[2 * b + 1] = 0; }
+        return 0;
+    }
+    if (batch == 0) return 0;
+    EMP_CK(cudaSetDevice(pl->device), "cudaSetDevice");
+    const size_t nb = (size_t)batch * n * 8;
+    double *d_lmin = pl->d_qp_in, *d_lmax = pl->d_qp_in + (size_t)batch * n, *d_start = pl->d_qp_in + 2 * (size_t)batch * n;
+    EMP_CK(cudaMemcpyAsync(d_lmin, l_min, nb, cudaMemcpyHostToDevice, pl->stream), "H2D lmin");
+    EMP_CK(cudaMemcpyAsync(d_lmax, l_max, nb, cudaMemcpyHostToDevice, pl->stream), "H2D lmax");
+    EMP_CK(cudaMemcpyAsync(d_start, start, (size_t)batch * 3 * 8, cudaMemcpyHostToDevice, pl->stream), "H2D start");
+    EMP_CK(cudaEventRecord(pl->ev0, pl->stream), "event");
+    int rc = emp_qp_dev(d_lmin, d_lmax, d_start, n, batch, p, pl->d_qp_out, pl->d_status, pl->stream);
+    if (rc) return rc;
+    EMP_CK(cudaEventRecord(pl->ev1, pl->stream), "event");
+    EMP_CK(cudaMemcpyAsync(out, pl->d_qp_out, (size_t)batch * 3 * n * 8, cudaMemcpyDeviceToHost, pl->stream), "D2H qp");
+    EMP_CK(cudaMemcpyAsync(status_iters, pl->d_status, (size_t)batch * 2 * 4, cudaMemcpyDeviceToHost, pl->stream), "D2H status");
+    EMP_CK(cudaStreamSynchronize(pl->stream), "planner stream");
+    cudaEventElapsedTime(&pl->last_ms, pl->ev0, pl->ev1);
+    return 0;
+}
+
+int emp_corridor_host(EmpPlanner *pl, const double *dp_s, const double *dp_l, int n, const double *scenes, int batch,
+                      const EmpQpParams *p, double *lmin_lmax, int32_t *status_iters) {
+    if (!pl || !dp_s || !dp_l || !scenes || !lmin_lmax || !status_iters) return fail(-1, "NULL argument");
+    if (batch < 0 || batch > pl->max_batch) return fail(-2, "batch exceeds planner capacity");
+    if (n < 1 || n > EMP_MAX_QP_POINTS) {
+        for (int b = 0; b < batch; ++b) { status_iters[2 * b] = EMP_QP_TOO_LARGE; status_iters[2 * b + 1] = 0; }
+        return 0;
+    }
+    if (batch == 0) return 0;
+    EMP_CK(cudaSetDevice(pl->device), "cudaSetDevice");
+    const size_t nb = (size_t)batch * n * 8;
+    const size_t sb = (size_t)batch * emp_scene_stride(pl->kmax) * 8;
+    double *d_s = pl->d_qp_in, *d_l = pl->d_qp_in + (size_t)batch * n;
+    EMP_CK(cudaMemcpyAsync(d_s, dp_s, nb, cudaMemcpyHostToDevice, pl->stream), "H2D dp_s");
+    EMP_CK(cudaMemcpyAsync(d_l, dp_l, nb, cudaMemcpyHostToDevice, pl->stream), "H2D dp_l");
+    EMP_CK(cudaMemcpyAsync(pl->d_scenes, scenes, sb, cudaMemcpyHostToDevice, pl->stream), "H2D scenes");
+    int rc = emp_corridor_dev(d_s, d_l, n, pl->d_scenes, pl->kmax, batch, p, pl->d_qp_out, pl->d_status, pl->stream);
+    if (rc) return rc;
+    EMP_CK(cudaMemcpyAsync(lmin_lmax, pl->d_qp_out, 2 * nb, cudaMemcpyDeviceToHost, pl->stream), "D2H corridor");
+    EMP_CK(cudaMemcpyAsync(status_iters, pl->d_status, (size_t)batch * 2 * 4, cudaMemcpyDeviceToHost, pl->stream), "D2H status");
+    EMP_CK(cudaStreamSynchronize(pl->stream), "planner stream");
+    return 0;
+}
+
+double emp_planner_last_kernel_ms(const EmpPlanner *pl) { return pl ? (double)pl->last_ms : 0.0; }
+
+}  // extern "C"

@@ -1,0 +1,612 @@
+// K2 - corridor + QP path smoother, one warp per ego frame, one lane per station.
+//
+// Replaces reference planner/path_planning.py cal_lmin_lmax (:222-273) and
+// Quadratic_planning (:78-219) including its cvxopt.solvers.qp call (:211-214).
+//
+// The QP   min 1/2 x'Px + q'x  s.t. Gx <= h, Ax = b   (x = (l,dl,ddl) per station)
+// is solved with the same Mehrotra predictor-corrector iteration as cvxopt's
+// coneqp (initial point, step rule STEP=0.99, sigma = (1-a+..)^3, stopping test
+// with abstol/reltol/feastol) so the iterates and the stopping iteration match
+// the CPU oracle (oracle/coneqp.py); only the linear algebra is different:
+//   * all 14 inequality rows of a station touch only that station's 3 variables,
+//     so S = P + G' diag(z/s) G is formed per lane; its (l,dl) 2x2 block is
+//     Cholesky-factored from the closed form of the rank-one sum (no cancellation
+//     when a corridor row or a start/end pin becomes stiff, z/s ~ 1e18);
+//   * the jerk coupling w_dddl*(ddl[i+1]-ddl[i])^2 is split off with an auxiliary
+//     equality row, which makes K = A S^-1 A' block tridiagonal (3x3 blocks):
+//     cvxopt's dense `chol2` becomes a block-Cholesky chain passed lane to lane
+//     with warp shuffles (forward/backward substitution likewise).
+// s, z are carried unscaled (mathematically identical to cvxopt's Nesterov-Todd
+// scaled iterates for the non-negative orthant).
+#include "emp_common.cuh"
+#include "sl_kernels.h"
+
+namespace emp {
+
+namespace {
+
+constexpr int NR = 14;          // inequality rows per station: 8 vehicle-corner rows + 3 ub + 3 lb
+#define EMP_UNROLL _Pragma("unroll")
+
+struct Geo {                    // per-launch constants of the dynamics / constraint geometry
+    double d1, d2;              // host_d1, host_d2 (levers of the corner rows, :117-124)
+    double a, b, e, g0;         // ds, ds^2/3, ds/2, ds^2/6   (:109-110)
+};
+
+// G x for one station (row order: 8 corner rows :117-124, then x <= ub, then -x <= -lb :163-166)
+__device__ __forceinline__ void gmul(const double x[3], const Geo &G, double o[NR]) {
+    const double pa = x[0] + G.d1 * x[1];
+    const double pb = x[0] - G.d2 * x[1];
+    o[0] = pa; o[1] = pa; o[2] = pb; o[3] = pb;
+    o[4] = -pa; o[5] = -pa; o[6] = -pb; o[7] = -pb;
+    o[8] = x[0]; o[9] = x[1]; o[10] = x[2];
+    o[11] = -x[0]; o[12] = -x[1]; o[13] = -x[2];
+}
+// G' v for one station
+__device__ __forceinline__ void gtmul(const double v[NR], const Geo &G, double o[3]) {
+    const double pa = (v[0] + v[1]) - (v[4] + v[5]);
+    const double pb = (v[2] + v[3]) - (v[6] + v[7]);
+    o[0] = (pa + pb) + (v[8] - v[11]);
+    o[1] = (G.d1 * pa - G.d2 * pb) + (v[9] - v[12]);
+    o[2] = v[10] - v[13];
+}
+
+template <int N>
+__device__ __forceinline__ void warp_sum_n(double (&v)[N]) {
+    EMP_UNROLL
+    for (int o = 16; o > 0; o >>= 1) {
+        EMP_UNROLL
+        for (int k = 0; k < N; ++k) v[k] += shfl_xor(v[k], o);
+    }
+}
+
+// first-minimum argmin over lanes (np.argmin semantics)
+__device__ __forceinline__ int warp_argmin(double v, int lane) {
+    int idx = lane;
+    EMP_UNROLL
+    for (int o = 16; o > 0; o >>= 1) {
+        const double ov = shfl_xor(v, o);
+        const int oi = __shfl_xor_sync(EMP_FULL_MASK, idx, o);
+        if (ov < v || (ov == v && oi < idx)) {
+            v = ov;
+            idx = oi;
+        }
+    }
+    return idx;
+}
+
+struct Factor {                 // per-lane pieces of the KKT factorisation
+    double q00, q01, q11, q22;  // Q upper triangular, S_i^-1 = Q Q'
+    double l00, l10, l11, l20, l21, l22;   // Cholesky block L_ii of stage i (pair i,i+1)
+    double i00, i11, i22;       // 1 / diag(L_ii)
+    double m[9];                // M_i = L_{i-1}^-1 (F X_i E'), row-major
+};
+
+__global__ void __launch_bounds__(QP_WARPS * 32)
+sl_qp_kernel(const double *__restrict__ scenes, double *__restrict__ plans, double *__restrict__ lmin_lmax,
+             const double *__restrict__ lmin_in, const double *__restrict__ lmax_in,
+             const double *__restrict__ start_in, double *__restrict__ out_x,
+             int32_t *__restrict__ status_iters, const QpLaunch p) {
+    const int lane = threadIdx.x & 31;
+    const int frame = blockIdx.x * QP_WARPS + (threadIdx.x >> 5);
+    if (frame >= p.batch) return;
+    const EmpQpParams &Q = p.q;
+
+    // ---------------- inputs ---------------------------------------------------
+    int n;
+    double lmin = -10.0, lmax = 10.0;             // path_planning.py:233-234
+    double st[3] = {0.0, 0.0, 0.0};
+    int qp_status = EMP_QP_OK;
+    double *plan = nullptr;
+    if (p.mode == QP_MODE_DIRECT) {
+        n = p.n_direct;
+        if (n > EMP_MAX_QP_POINTS || n < 2) qp_status = EMP_QP_TOO_LARGE;
+        if (lane < n && qp_status == EMP_QP_OK) {
+            lmin = lmin_in[(size_t)frame * n + lane];
+            lmax = lmax_in[(size_t)frame * n + lane];
+        }
+        st[0] = start_in[(size_t)frame * 3 + 0];
+        st[1] = start_in[(size_t)frame * 3 + 1];
+        st[2] = start_in[(size_t)frame * 3 + 2];
+    } else {
+        const double *sc = scenes + (size_t)frame * p.scene_stride;
+        const int NE = p.n_enr_max;
+        double dps = 0.0, dpl = 0.0;
+        int nq_out;
+        if (p.mode == QP_MODE_FUSED) {
+            plan = plans + (size_t)frame * p.plan_stride;
+            const int n_enr = (int)plan[0];
+            n = (n_enr + 1) >> 1;                  // dp_path[::2]  (test_9.py:187-188)
+            nq_out = (NE + 1) / 2;
+            st[0] = sc[1];
+            st[1] = sc[2];
+            st[2] = sc[3];
+        } else {                                   // QP_MODE_CORRIDOR: path given by the caller
+            n = p.n_direct;
+            nq_out = n;
+        }
+        if (n > EMP_MAX_QP_POINTS || n < (p.mode == QP_MODE_FUSED ? 2 : 1)) qp_status = EMP_QP_TOO_LARGE;
+        const bool valid0 = lane < n && qp_status == EMP_QP_OK;
+        if (valid0) {
+            if (p.mode == QP_MODE_FUSED) {
+                dps = plan[EMP_PLAN_HDR + 2 * lane];
+                dpl = plan[EMP_PLAN_HDR + NE + 2 * lane];
+            } else {
+                dps = lmin_in[(size_t)frame * n + lane];
+                dpl = lmax_in[(size_t)frame * n + lane];
+            }
+        }
+        // ---- cal_lmin_lmax (:222-273)
+        int K = (int)sc[4];
+        K = K < 0 ? 0 : (K > p.kmax ? p.kmax : K);
+        const double INF = __longlong_as_double(0x7ff0000000000000LL);
+        if (qp_status == EMP_QP_OK) {
+            for (int o = 0; o < K; ++o) {
+                const double os = sc[EMP_SCENE_HDR + o];
+                const double ol = sc[EMP_SCENE_HDR + p.kmax + o];
+                const double smin = os - Q.obs_length / 2;
+                const double smax = os + Q.obs_length / 2;
+                const int lo = warp_argmin(valid0 ? fabs(dps - smin) : INF, lane) + 2;   // offset = 2 (:235,:240)
+                const int hi = warp_argmin(valid0 ? fabs(dps - smax) : INF, lane) + 2;
+                const int ctr = warp_argmin(valid0 ? fabs(dps - os) : INF, lane);
+                const double path_l = shfl(dpl, ctr);
+                if (lo <= hi && hi >= n) {         // the reference raises IndexError here (:265-272)
+                    qp_status = EMP_QP_CORRIDOR_INDEX;
+                    break;
+                }
+                if (lane >= lo && lane <= hi) {
+                    if (path_l < ol) lmax = fmin(lmax, ol - Q.obs_width / 2);
+                    else lmin = fmax(lmin, ol + Q.obs_width / 2);
+                }
+            }
+        }
+        if (lmin_lmax != nullptr && lane < nq_out) {
+            lmin_lmax[((size_t)frame * 2 + 0) * nq_out + lane] = lane < n ? lmin : 0.0;
+            lmin_lmax[((size_t)frame * 2 + 1) * nq_out + lane] = lane < n ? lmax : 0.0;
+        }
+        if (p.mode == QP_MODE_CORRIDOR) {
+            if (lane == 0) {
+                status_iters[2 * frame] = qp_status;
+                status_iters[2 * frame + 1] = 0;
+            }
+            return;
+        }
+    }
+
+    int iters = 0;
+    double gap = 0.0;
+    double x[3] = {0.0, 0.0, 0.0};
+
+    if (qp_status == EMP_QP_OK) {
+        const bool valid = lane < n;
+        const bool stage = lane < n - 1;           // lane i owns equality pair (i, i+1)
+        const int m_rows = NR * n;
+        // ---------------- problem data (Quadratic_planning :103-205) -----------
+        Geo G;
+        G.d1 = Q.host_d1;
+        G.d2 = Q.host_d2;
+        const double ds = Q.dp_sampling_res;
+        G.a = ds;
+        G.b = ds * ds / 3;
+        G.e = ds / 2;
+        G.g0 = ds * ds / 6;
+        const int fi = (int)ceil(Q.host_d1 / ds), bi = (int)ceil(Q.host_d2 / ds);
+        const double hU = shfl(lmax, min(lane + fi, n - 1));     // l_max[index1] (:130)
+        const double hL = shfl(lmin, max(lane - bi, 0));         // l_min[index2] (:131)
+        const double hw = Q.host_w / 2;
+        double h[NR];
+        h[0] = hU - hw; h[1] = hU + hw; h[2] = hU - hw; h[3] = hU + hw;
+        h[4] = -hL + hw; h[5] = -hL - hw; h[6] = -hL + hw; h[7] = -hL - hw;
+        EMP_UNROLL
+        for (int c = 0; c < 3; ++c) {
+            double ub = 100000.0, nlb = 100000.0;                // :145-147
+            if (lane == 0) { ub = st[c]; nlb = -st[c]; }         // :148-153
+            if (lane == n - 1) { ub = 0.0; nlb = 0.0; }          // :155-160
+            h[8 + c] = ub;
+            h[11 + c] = nlb;
+        }
+        // P (diagonal part) with and without the jerk terms; cc = coupling ddl_i <-> ddl_{i+1}
+        double Pd[3], Pn[3];
+        Pd[0] = 2 * (Q.w_l + Q.w_centre);
+        Pd[1] = 0.0;                                             // w_cost_dl*(H_DL.T@H_L) == 0 (:193)
+        Pn[2] = 2 * Q.w_ddl;
+        if (lane == n - 1) {
+            Pd[0] += 2 * Q.w_end_l;
+            Pd[1] += 2 * Q.w_end_dl;
+            Pn[2] += 2 * Q.w_end_ddl;
+        }
+        Pn[0] = Pd[0];
+        Pn[1] = Pd[1];
+        Pd[2] = Pn[2] + 2 * Q.w_dddl * ((lane == 0 || lane == n - 1) ? 1.0 : 2.0);
+        const double cc = -2 * Q.w_dddl;
+        const bool nojerk = !(Q.w_dddl > 0.0);
+        const double jinv = nojerk ? 1.0 : 1.0 / (2 * Q.w_dddl);
+        const double q0 = valid ? Q.w_centre * (-2 * ((lmin + lmax) / 2)) : 0.0;   // :199-205
+
+        // ---------------- helpers ------------------------------------------------
+        Factor F;
+        bool broke = false;
+
+        // factor(w): per-lane S^-1 = QQ', then the block-Cholesky chain of K
+        auto factor = [&](const double w[NR]) {
+            const double wa = (w[0] + w[1]) + (w[4] + w[5]);
+            const double wb = (w[2] + w[3]) + (w[6] + w[7]);
+            const double D0 = Pn[0] + (w[8] + w[11]);
+            const double D1 = Pn[1] + (w[9] + w[12]);
+            const double s22 = Pn[2] + (w[10] + w[13]);
+            const double s01 = G.d1 * wa - G.d2 * wb;
+            const double r00sq = D0 + (wa + wb);
+            const double dsum = G.d1 + G.d2;
+            const double r11sq = D1 + (D0 * (G.d1 * G.d1 * wa + G.d2 * G.d2 * wb) + (wa * wb) * (dsum * dsum)) / r00sq;
+            const double ir00 = rsqrt(r00sq);
+            const double ir11 = rsqrt(r11sq);
+            F.q00 = ir00;
+            F.q11 = ir11;
+            F.q01 = -(s01 * ir00) * (ir00 * ir11);
+            F.q22 = rsqrt(s22);
+            if (!valid) { F.q00 = 1.0; F.q11 = 1.0; F.q01 = 0.0; F.q22 = 1.0; }
+            // U = E Q, V = F Q
+            const double u01 = F.q01 + G.a * F.q11, u02 = G.b * F.q22, u12 = G.e * F.q22, v02 = G.g0 * F.q22;
+            double e00 = F.q00 * F.q00 + u01 * u01 + u02 * u02;
+            double e10 = u01 * F.q11 + u02 * u12;
+            double e11 = F.q11 * F.q11 + u12 * u12;
+            double e20 = u02 * F.q22, e21 = u12 * F.q22, e22 = F.q22 * F.q22;
+            double f00 = F.q00 * F.q00 + F.q01 * F.q01 + v02 * v02;
+            double f10 = F.q01 * F.q11 + v02 * u12;
+            double f11 = e11;
+            double f20 = -v02 * F.q22, f21 = -u12 * F.q22, f22 = e22;
+            double B[9];                                           // F X_i E' = V U'
+            B[0] = (v02 * u02 - F.q00 * F.q00) - F.q01 * u01;
+            B[1] = v02 * u12 - F.q01 * F.q11;
+            B[2] = v02 * F.q22;
+            B[3] = u12 * u02 - F.q11 * u01;
+            B[4] = u12 * u12 - F.q11 * F.q11;
+            B[5] = u12 * F.q22;
+            B[6] = -F.q22 * u02;
+            B[7] = -F.q22 * u12;
+            B[8] = -e22;
+            if (nojerk) {
+                e20 = e21 = 0.0; f20 = f21 = 0.0; e22 = 0.0; f22 = 0.0;
+                B[2] = B[5] = B[6] = B[7] = B[8] = 0.0;
+            }
+            // K_ii = E X_i E' + F X_{i+1} F' + diag(0,0,1/(2 w_dddl))
+            const double k00 = e00 + shfl_down(f00, 1);
+            const double k10 = e10 + shfl_down(f10, 1);
+            const double k11 = e11 + shfl_down(f11, 1);
+            const double k20 = e20 + shfl_down(f20, 1);
+            const double k21 = e21 + shfl_down(f21, 1);
+            const double k22 = (e22 + shfl_down(f22, 1)) + jinv;
+            F.l00 = 1.0; F.l10 = 0.0; F.l11 = 1.0; F.l20 = 0.0; F.l21 = 0.0; F.l22 = 1.0;
+            F.i00 = 1.0; F.i11 = 1.0; F.i22 = 1.0;
+            EMP_UNROLL
+            for (int k = 0; k < 9; ++k) F.m[k] = 0.0;
+            bool bad = false;
+            for (int i = 0; i < n - 1; ++i) {
+                const int src = i > 0 ? i - 1 : 0;
+                const double pl10 = shfl(F.l10, src), pl20 = shfl(F.l20, src), pl21 = shfl(F.l21, src);
+                const double pi00 = shfl(F.i00, src), pi11 = shfl(F.i11, src), pi22 = shfl(F.i22, src);
+                double M[9];
+                EMP_UNROLL
+                for (int c = 0; c < 3; ++c) {                     // M = L_{i-1}^-1 B, column c
+                    const double m0 = B[c] * pi00;
+                    const double m1 = (B[3 + c] - pl10 * m0) * pi11;
+                    const double m2 = ((B[6 + c] - pl20 * m0) - pl21 * m1) * pi22;
+                    M[c] = i > 0 ? m0 : 0.0;
+                    M[3 + c] = i > 0 ? m1 : 0.0;
+                    M[6 + c] = i > 0 ? m2 : 0.0;
+                }
+                // D = K_ii - M'M
+                const double d00 = k00 - (M[0] * M[0] + M[3] * M[3] + M[6] * M[6]);
+                const double d10 = k10 - (M[1] * M[0] + M[4] * M[3] + M[7] * M[6]);
+                const double d11 = k11 - (M[1] * M[1] + M[4] * M[4] + M[7] * M[7]);
+                const double d20 = k20 - (M[2] * M[0] + M[5] * M[3] + M[8] * M[6]);
+                const double d21 = k21 - (M[2] * M[1] + M[5] * M[4] + M[8] * M[7]);
+                const double d22 = k22 - (M[2] * M[2] + M[5] * M[5] + M[8] * M[8]);
+                const double j00 = rsqrt(d00);
+                const double c10 = d10 * j00, c20 = d20 * j00;
+                const double t11 = d11 - c10 * c10;
+                const double j11 = rsqrt(t11);
+                const double c21 = (d21 - c20 * c10) * j11;
+                const double t22 = (d22 - c20 * c20) - c21 * c21;
+                const double j22 = rsqrt(t22);
+                if (lane == i) {
+                    bad = !(d00 > 0.0) || !(t11 > 0.0) || !(t22 > 0.0) || !isfinite(j00 + j11 + j22);
+                    F.l00 = d00 * j00; F.l10 = c10; F.l11 = t11 * j11; F.l20 = c20; F.l21 = c21; F.l22 = t22 * j22;
+                    F.i00 = j00; F.i11 = j11; F.i22 = j22;
+                    EMP_UNROLL
+                    for (int k = 0; k < 9; ++k) F.m[k] = M[k];
+                }
+            }
+            broke = __any_sync(EMP_FULL_MASK, bad);
+        };
+
+        // solve [S A'; A 0][dx; dy] = [g; by] with the current factorisation
+        auto kkt_solve = [&](const double g[3], const double by[2], double dx[3], double dy[2]) {
+            // X g = Q (Q' g)
+            auto applyX = [&](const double v[3], double o[3]) {
+                const double t0 = F.q00 * v[0];
+                const double t1 = F.q01 * v[0] + F.q11 * v[1];
+                const double t2 = F.q22 * v[2];
+                o[0] = F.q00 * t0 + F.q01 * t1;
+                o[1] = F.q11 * t1;
+                o[2] = F.q22 * t2;
+            };
+            double xg[3];
+            applyX(g, xg);
+            // r_i = E Xg_i + F Xg_{i+1} - (by, 0)
+            const double fx0 = -xg[0] + G.g0 * xg[2];
+            const double fx1 = -xg[1] + G.e * xg[2];
+            const double fx2 = -xg[2];
+            double r0 = ((xg[0] + G.a * xg[1]) + G.b * xg[2]) + shfl_down(fx0, 1) - by[0];
+            double r1 = (xg[1] + G.e * xg[2]) + shfl_down(fx1, 1) - by[1];
+            double r2 = nojerk ? 0.0 : xg[2] + shfl_down(fx2, 1);
+            // forward substitution chain  t_i = L_ii^-1 (r_i - M_i' t_{i-1})
+            double t0 = 0.0, t1 = 0.0, t2 = 0.0;
+            for (int i = 0; i < n - 1; ++i) {
+                const int src = i > 0 ? i - 1 : 0;
+                double p0 = shfl(t0, src), p1 = shfl(t1, src), p2 = shfl(t2, src);
+                if (i == 0) { p0 = 0.0; p1 = 0.0; p2 = 0.0; }
+                const double rr0 = r0 - ((F.m[0] * p0 + F.m[3] * p1) + F.m[6] * p2);
+                const double rr1 = r1 - ((F.m[1] * p0 + F.m[4] * p1) + F.m[7] * p2);
+                const double rr2 = r2 - ((F.m[2] * p0 + F.m[5] * p1) + F.m[8] * p2);
+                const double c0 = rr0 * F.i00;
+                const double c1 = (rr1 - F.l10 * c0) * F.i11;
+                const double c2 = ((rr2 - F.l20 * c0) - F.l21 * c1) * F.i22;
+                if (lane == i) { t0 = c0; t1 = c1; t2 = c2; }
+            }
+            // backward substitution chain  y_i = L_ii^-T (t_i - M_{i+1} y_{i+1})
+            double y0 = 0.0, y1 = 0.0, y2 = 0.0, cd0 = 0.0, cd1 = 0.0, cd2 = 0.0;
+            for (int i = n - 2; i >= 0; --i) {
+                const int src = i + 1;
+                double u0 = shfl(cd0, src), u1 = shfl(cd1, src), u2 = shfl(cd2, src);
+                if (i == n - 2) { u0 = 0.0; u1 = 0.0; u2 = 0.0; }
+                const double rr0 = t0 - u0, rr1 = t1 - u1, rr2 = t2 - u2;
+                const double c2 = rr2 * F.i22;
+                const double c1 = (rr1 - F.l21 * c2) * F.i11;
+                const double c0 = ((rr0 - F.l10 * c1) - F.l20 * c2) * F.i00;
+                if (lane == i) {
+                    y0 = c0; y1 = c1; y2 = c2;
+                    cd0 = (F.m[0] * c0 + F.m[1] * c1) + F.m[2] * c2;
+                    cd1 = (F.m[3] * c0 + F.m[4] * c1) + F.m[5] * c2;
+                    cd2 = (F.m[6] * c0 + F.m[7] * c1) + F.m[8] * c2;
+                }
+            }
+            if (!stage) { y0 = 0.0; y1 = 0.0; y2 = 0.0; }
+            // x = X (g - E' y_i - F' y_{i-1})
+            double pu0 = shfl_up(y0, 1), pu1 = shfl_up(y1, 1), pu2 = shfl_up(y2, 1);
+            if (lane == 0) { pu0 = 0.0; pu1 = 0.0; pu2 = 0.0; }
+            double v[3];
+            v[0] = g[0] - (y0 - pu0);
+            v[1] = g[1] - ((G.a * y0 + y1) - pu1);
+            v[2] = g[2] - (((G.b * y0 + G.e * y1) + y2) + ((G.g0 * pu0 + G.e * pu1) - pu2));
+            applyX(v, dx);
+            dy[0] = y0;
+            dy[1] = y1;
+        };
+
+        // P x (with the jerk coupling), A x, A' y
+        auto pmul = [&](const double xx[3], double o[3]) {
+            double up = shfl_up(xx[2], 1), dn = shfl_down(xx[2], 1);
+            if (lane == 0) up = 0.0;
+            if (lane >= n - 1) dn = 0.0;
+            o[0] = Pd[0] * xx[0];
+            o[1] = Pd[1] * xx[1];
+            o[2] = Pd[2] * xx[2] + cc * (up + dn);
+        };
+        auto amul = [&](const double xx[3], double o[2]) {
+            const double n0 = shfl_down(xx[0], 1), n1 = shfl_down(xx[1], 1), n2 = shfl_down(xx[2], 1);
+            o[0] = stage ? (((xx[0] + G.a * xx[1]) + G.b * xx[2]) - n0) + G.g0 * n2 : 0.0;
+            o[1] = stage ? ((xx[1] + G.e * xx[2]) - n1) + G.e * n2 : 0.0;
+        };
+        auto atmul = [&](const double yy[2], double o[3]) {
+            double p0 = shfl_up(yy[0], 1), p1 = shfl_up(yy[1], 1);
+            if (lane == 0) { p0 = 0.0; p1 = 0.0; }
+            o[0] = yy[0] - p0;
+            o[1] = (G.a * yy[0] + yy[1]) - p1;
+            o[2] = (G.b * yy[0] + G.e * yy[1]) + (G.g0 * p0 + G.e * p1);
+        };
+
+        // ---------------- initial point (coneqp: W = I) --------------------------
+        double s[NR], z[NR], y[2] = {0.0, 0.0};
+        {
+            double w1[NR];
+            EMP_UNROLL
+            for (int r = 0; r < NR; ++r) w1[r] = 1.0;
+            factor(w1);
+            double g[3], gth[3], by[2] = {0.0, 0.0};
+            gtmul(h, G, gth);
+            g[0] = -q0 + gth[0];
+            g[1] = gth[1];
+            g[2] = gth[2];
+            if (!valid) { g[0] = g[1] = g[2] = 0.0; }
+            kkt_solve(g, by, x, y);
+            double gx[NR];
+            gmul(x, G, gx);
+            double red[2] = {0.0, 0.0};
+            double mn_s = -1e300, mn_z = -1e300;                   // max(-s), max(-z)
+            EMP_UNROLL
+            for (int r = 0; r < NR; ++r) {
+                z[r] = valid ? gx[r] - h[r] : 1.0;
+                s[r] = valid ? -z[r] : 1.0;
+                if (valid) {
+                    red[0] += s[r] * s[r];
+                    mn_s = fmax(mn_s, -s[r]);
+                    mn_z = fmax(mn_z, -z[r]);
+                }
+            }
+            warp_sum_n(red);
+            const double nrm = sqrt(red[0]);                       // ||s|| == ||z||
+            const double ts = warp_max(mn_s), tz = warp_max(mn_z);
+            if (ts >= -1e-8 * fmax(nrm, 1.0)) {
+                EMP_UNROLL
+                for (int r = 0; r < NR; ++r) s[r] = valid ? s[r] + (1.0 + ts) : 1.0;
+            }
+            if (tz >= -1e-8 * fmax(nrm, 1.0)) {
+                EMP_UNROLL
+                for (int r = 0; r < NR; ++r) z[r] = valid ? z[r] + (1.0 + tz) : 1.0;
+            }
+            double gs = 0.0;
+            EMP_UNROLL
+            for (int r = 0; r < NR; ++r) gs += valid ? s[r] * z[r] : 0.0;
+            gap = warp_sum(gs);
+        }
+        double n0[2] = {valid ? q0 * q0 : 0.0, 0.0};
+        EMP_UNROLL
+        for (int r = 0; r < NR; ++r) n0[1] += valid ? h[r] * h[r] : 0.0;
+        warp_sum_n(n0);
+        const double resx0 = fmax(1.0, sqrt(n0[0]));
+        const double resy0 = 1.0;                                  // b = 0
+        const double resz0 = fmax(1.0, sqrt(n0[1]));
+        if (broke) qp_status = EMP_QP_UNKNOWN_NUMERIC;             // cvxopt raises ValueError here
+
+        // ---------------- main loop ----------------------------------------------
+        double ws3[NR];
+        while (qp_status == EMP_QP_OK) {
+            double rx[3], ry[2], rz[NR];
+            double pxq[3], aty[3], gtz[3], gx[NR];
+            pmul(x, pxq);
+            pxq[0] += q0;
+            atmul(y, aty);
+            gtmul(z, G, gtz);
+            amul(x, ry);
+            gmul(x, G, gx);
+            double red[7] = {0, 0, 0, 0, 0, 0, 0};
+            EMP_UNROLL
+            for (int c = 0; c < 3; ++c) {
+                rx[c] = valid ? (pxq[c] + aty[c]) + gtz[c] : 0.0;
+                red[0] += rx[c] * rx[c];
+                red[3] += valid ? x[c] * pxq[c] : 0.0;
+            }
+            red[4] = valid ? x[0] * q0 : 0.0;
+            red[1] = ry[0] * ry[0] + ry[1] * ry[1];
+            red[5] = y[0] * ry[0] + y[1] * ry[1];
+            EMP_UNROLL
+            for (int r = 0; r < NR; ++r) {
+                rz[r] = valid ? (s[r] + gx[r]) - h[r] : 0.0;
+                red[2] += rz[r] * rz[r];
+                red[6] += valid ? z[r] * rz[r] : 0.0;
+            }
+            warp_sum_n(red);
+            const double resx = sqrt(red[0]), resy = sqrt(red[1]), resz = sqrt(red[2]);
+            const double pcost = 0.5 * (red[3] + red[4]);
+            const double dcost = ((pcost + red[5]) + red[6]) - gap;
+            bool have_rel = true;
+            double relgap = 0.0;
+            if (pcost < 0.0) relgap = gap / -pcost;
+            else if (dcost > 0.0) relgap = gap / dcost;
+            else have_rel = false;
+            const double pres = fmax(resy / resy0, resz / resz0);
+            const double dres = resx / resx0;
+            if (pres <= Q.feastol && dres <= Q.feastol && (gap <= Q.abstol || (have_rel && relgap <= Q.reltol))) break;
+            if (iters == Q.maxiters) { qp_status = EMP_QP_UNKNOWN_MAXITER; break; }
+            if (!isfinite((gap + resx) + resz)) { qp_status = EMP_QP_UNKNOWN_NUMERIC; break; }
+
+            double is[NR], w[NR];
+            EMP_UNROLL
+            for (int r = 0; r < NR; ++r) {
+                is[r] = 1.0 / s[r];
+                w[r] = z[r] * is[r];
+            }
+            factor(w);
+            if (broke) { qp_status = EMP_QP_UNKNOWN_NUMERIC; break; }   // cvxopt: ArithmeticError -> 'unknown'
+
+            const double mu = gap / (double)m_rows;
+            double sigma = 0.0, step = 1.0;
+            double dx[3], dy[2], dsv[NR], dz[NR];
+            EMP_UNROLL
+            for (int pass = 0; pass < 2; ++pass) {
+                double tq[NR], gtq[3], g[3], by[2];
+                EMP_UNROLL
+                for (int r = 0; r < NR; ++r) {
+                    double bs = sigma * mu - s[r] * z[r];
+                    if (pass == 1) bs -= ws3[r];
+                    tq[r] = valid ? (bs + z[r] * rz[r]) * is[r] : 0.0;
+                }
+                gtmul(tq, G, gtq);
+                EMP_UNROLL
+                for (int c = 0; c < 3; ++c) g[c] = -rx[c] - gtq[c];
+                by[0] = -ry[0];
+                by[1] = -ry[1];
+                kkt_solve(g, by, dx, dy);
+                double gdx[NR];
+                gmul(dx, G, gdx);
+                double dsdz = 0.0, ts = -1e300, tz = -1e300;
+                EMP_UNROLL
+                for (int r = 0; r < NR; ++r) {
+                    dz[r] = tq[r] + w[r] * gdx[r];
+                    dsv[r] = -rz[r] - gdx[r];
+                    if (valid) {
+                        dsdz += dsv[r] * dz[r];
+                        ts = fmax(ts, -dsv[r] * is[r]);
+                        tz = fmax(tz, -dz[r] / z[r]);
+                    }
+                    if (pass == 0) ws3[r] = dsv[r] * dz[r];
+                }
+                dsdz = warp_sum(dsdz);
+                const double t = fmax(0.0, warp_max(fmax(ts, tz)));
+                if (t == 0.0) step = 1.0;
+                else step = pass == 0 ? fmin(1.0, 1.0 / t) : fmin(1.0, 0.99 / t);
+                if (pass == 0) {
+                    const double sg = fmin(1.0, fmax(0.0, (1.0 - step) + (dsdz / gap) * (step * step)));
+                    sigma = (sg * sg) * sg;
+                }
+            }
+            EMP_UNROLL
+            for (int c = 0; c < 3; ++c) x[c] += step * dx[c];
+            y[0] += step * dy[0];
+            y[1] += step * dy[1];
+            double gs = 0.0;
+            EMP_UNROLL
+            for (int r = 0; r < NR; ++r) {
+                if (valid) {
+                    s[r] += step * dsv[r];
+                    z[r] += step * dz[r];
+                    gs += s[r] * z[r];
+                }
+            }
+            gap = warp_sum(gs);
+            ++iters;
+        }
+    }
+
+    // ---------------- outputs ----------------------------------------------------
+    if (plan != nullptr) {
+        const int NE = p.n_enr_max, NQ = (NE + 1) / 2;
+        double *o = plan + EMP_PLAN_HDR + 2 * NE;
+        if (lane < n && lane < NQ) {
+            o[lane] = x[0];
+            o[NQ + lane] = x[1];
+            o[2 * NQ + lane] = x[2];
+        }
+        if (lane == 0) {
+            plan[1] = (double)n;
+            plan[3] = (double)qp_status;
+            plan[4] = (double)iters;
+            plan[6] = gap;
+        }
+    } else {
+        if (lane < n && n <= EMP_MAX_QP_POINTS) {
+            double *o = out_x + (size_t)frame * 3 * n;
+            o[lane] = x[0];
+            o[n + lane] = x[1];
+            o[2 * n + lane] = x[2];
+        }
+        if (lane == 0) {
+            status_iters[2 * frame] = qp_status;
+            status_iters[2 * frame + 1] = iters;
+        }
+    }
+}
+
+}  // namespace
+
+cudaError_t launch_sl_qp(const double *scenes, double *plans, double *lmin_lmax, const double *lmin_in,
+                         const double *lmax_in, const double *start_in, double *out_x, int32_t *status_iters,
+                         const QpLaunch &p, cudaStream_t st) {
+    const int grid = (p.batch + QP_WARPS - 1) / QP_WARPS;
+    sl_qp_kernel<<<grid, QP_WARPS * 32, 0, st>>>(scenes, plans, lmin_lmax, lmin_in, lmax_in, start_in, out_x,
+                                                 status_iters, p);
+    return cudaGetLastError();
+}
+
+}  // namespace emp

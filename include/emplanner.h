@@ -1,0 +1,162 @@
+/*
+ * emplanner.h - C ABI of libemplanner.so: the B200 (sm_100a) implementation of the
+ * Frenet EM-planner hot path of 6Lackiu/EMplanner_Carla @ 1f115a5.
+ *
+ * The reference has no FFI: its boundary is the set of module-level Python
+ * functions in planner/path_planning.py, planner/planning_utils.py and
+ * planner/speed_planning_test.py.  Each entry point below cites the reference
+ * function(s) it replaces; emplanner_carla_b200/planner/*.py binds them with
+ * ctypes under the reference's own function names.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; no C++/torch types.
+ *   - `*_dev` entry points take DEVICE pointers and a cudaStream_t (as void*);
+ *     they only enqueue work.  `*_host` entry points take HOST pointers, own a
+ *     device workspace inside an EmpPlanner handle, and return after the result
+ *     is in the host buffers.
+ *   - return value: 0 = ok, <0 = error (emp_last_error() gives the text).
+ *     Per-frame algorithmic conditions are reported in per-frame status words,
+ *     never through the return value.
+ *   - all arithmetic is IEEE float64, like the reference (numpy float64).
+ */
+#ifndef EMPLANNER_H_
+#define EMPLANNER_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define EMP_VERSION 100          /* 0.1.0 */
+#define EMP_NSAMPLE 10           /* samples per lattice edge, path_planning.py:486,559 */
+#define EMP_MAX_ROW 16           /* lattice rows supported by the DP kernel */
+#define EMP_MAX_KMAX 32          /* obstacle slots per scene record */
+#define EMP_MAX_QP_POINTS 32     /* QP stations per frame (one warp lane each) */
+
+/* ---- per-frame status bits ------------------------------------------------ */
+#define EMP_DP_NO_OBSTACLE      0x1   /* K == 0: straight branch, path_planning.py:362-363 */
+#define EMP_DP_ALL_COLLIDE      0x2   /* final cost > w_collision: the reference prints its banner, :351-353 */
+#define EMP_DP_OVERFLOW         0x4   /* densified path longer than n_enr_max (output truncated) */
+#define EMP_QP_OK               0     /* 'optimal' */
+#define EMP_QP_UNKNOWN_MAXITER  1     /* cvxopt status 'unknown' after maxiters */
+#define EMP_QP_UNKNOWN_NUMERIC  2     /* 'unknown': factorisation breakdown / non-finite iterate */
+#define EMP_QP_CORRIDOR_INDEX   4     /* cal_lmin_lmax would raise IndexError, path_planning.py:265-272 */
+#define EMP_QP_TOO_LARGE        8     /* more than EMP_MAX_QP_POINTS stations, or fewer than 2 */
+
+/* ---- parameters (defaults = the reference's keyword defaults) -------------- */
+typedef struct EmpDpParams {          /* DP_algorithm, path_planning.py:276-279 */
+    double sampling_res;              /* 2 */
+    double w_collision;               /* 1e12 */
+    double w_smooth[3];               /* 300, 1000, 5000 */
+    double w_ref;                     /* 20 */
+    double sample_s;                  /* 15 */
+    double sample_l;                  /* 1.5 */
+    int32_t row;                      /* 12 */
+    int32_t col;                      /* 6 */
+} EmpDpParams;
+
+typedef struct EmpQpParams {          /* Quadratic_planning :78-81, cal_lmin_lmax :222, cvxopt defaults */
+    double dp_sampling_res;           /* 2 */
+    double w_l, w_dl, w_ddl, w_dddl;  /* 1000, 10000 (unused: :193), 3000, 150 */
+    double w_centre;                  /* 250 */
+    double w_end_l, w_end_dl, w_end_ddl; /* 40, 40, 40 */
+    double host_d1, host_d2, host_w;  /* 3, 3, 3 */
+    double obs_length, obs_width;     /* 5, 5 (test_9.py:190-193) */
+    double abstol, reltol, feastol;   /* 1e-7, 1e-6, 1e-7 */
+    int32_t maxiters;                 /* 100 */
+    int32_t reserved;
+} EmpQpParams;
+
+void emp_dp_params_default(EmpDpParams *p);
+void emp_qp_params_default(EmpQpParams *p);
+
+/* ---- data layouts ----------------------------------------------------------
+ * Scene record (input), float64 words, stride = emp_scene_stride(kmax):
+ *   [0] plan_start_s  [1] plan_start_l  [2] plan_start_dl  [3] plan_start_ddl
+ *   [4] number of obstacles K (0..kmax)   [5] reserved
+ *   [6 .. 6+kmax)         obs_s   (entries >= K ignored)
+ *   [6+kmax .. 6+2*kmax)  obs_l
+ * kmax must be even (records stay 16-byte aligned for the bulk copy).
+ *
+ * Plan record (output), float64 words, stride = emp_plan_stride(n_enr_max):
+ *   [0] n_enr   [1] n_qp   [2] dp status bits   [3] qp status   [4] qp iterations
+ *   [5] DP final cost   [6] final duality gap   [7] reserved
+ *   [8 .. 8+NE)                 enriched s   (DP_algorithm output, first n_enr valid)
+ *   [8+NE .. 8+2NE)             enriched l
+ *   [8+2NE .. 8+2NE+NQ)         qp_path_l    (first n_qp valid), NQ = (NE+1)/2
+ *   [.. +NQ)                    qp_path_dl
+ *   [.. +NQ)                    qp_path_ddl
+ * with NE = n_enr_max; stride rounded up to an even word count.
+ */
+int emp_scene_stride(int kmax);
+int emp_plan_stride(int n_enr_max);
+int emp_max_enriched(const EmpDpParams *p);   /* upper bound on n_enr for these lattice parameters */
+
+int emp_version(void);
+const char *emp_last_error(void);
+
+/* ---- device-pointer entry points -------------------------------------------*/
+
+/* S-L lattice DP + densify for a batch of frames, one launch.
+ * Replaces path_planning.DP_algorithm (:276-375) with cal_start_cost (:435),
+ * cal_neighbor_cost (:517), cal_obs_cost (:588), enrich_DP_s_l (:378) and
+ * planning_utils.cal_quintic_coefficient (:671).
+ * scenes: [batch, emp_scene_stride(kmax)]; plans: [batch, emp_plan_stride(n_enr_max)]
+ * (words 0,2,5 and the enriched arrays are written); rows: optional [batch, col]
+ * int32 lattice row per column (-1 for K == 0 frames), may be NULL. */
+int emp_sl_dp_dev(const double *scenes, int kmax, int batch, const EmpDpParams *p,
+                  int n_enr_max, double *plans, int32_t *rows, void *stream);
+
+/* Corridor + QP smoother for a batch, one launch; reads the enriched path that
+ * emp_sl_dp_dev left in `plans`, takes every 2nd point (test_9.py:187-188).
+ * Replaces path_planning.cal_lmin_lmax (:222-273) and Quadratic_planning
+ * (:78-219, incl. the cvxopt.solvers.qp call :211).  Writes words 1,3,4,6 and
+ * the qp arrays of each plan record.  lmin_lmax: optional [batch, 2, NQ] copy of
+ * the corridor, may be NULL. */
+int emp_sl_qp_dev(const double *scenes, int kmax, int batch, const EmpQpParams *p,
+                  int n_enr_max, double *plans, double *lmin_lmax, void *stream);
+
+/* Quadratic_planning alone on caller-supplied corridors (l_min/l_max: [batch, n]). */
+int emp_qp_dev(const double *l_min, const double *l_max, const double *start_l_dl_ddl /*[batch,3]*/,
+               int n, int batch, const EmpQpParams *p, double *out_l_dl_ddl /*[batch,3,n]*/,
+               int32_t *status_iters /*[batch,2]*/, void *stream);
+
+/* cal_lmin_lmax alone (:222-273) on caller-supplied paths dp_s/dp_l: [batch, n]; obstacles come
+ * from the scene records.  lmin_lmax: [batch, 2, n]; status_iters[2b] = 0 or EMP_QP_CORRIDOR_INDEX. */
+int emp_corridor_dev(const double *dp_s, const double *dp_l, int n, const double *scenes, int kmax, int batch,
+                     const EmpQpParams *p, double *lmin_lmax, int32_t *status_iters, void *stream);
+
+/* DP -> [::2] -> corridor -> QP: the S-L planning step (two launches on `stream`). */
+int emp_sl_plan_dev(const double *scenes, int kmax, int batch, const EmpDpParams *dp,
+                    const EmpQpParams *qp, int n_enr_max, double *plans, int32_t *rows, void *stream);
+
+/* FP64 FMA micro-benchmark (roofline denominator; absent from MEASURED_PEAKS.json).
+ * Returns achieved TFLOP/s through *tflops. */
+int emp_fp64_peak(int iters, double *tflops, double *ms);
+
+/* ---- host-buffer entry points ----------------------------------------------*/
+typedef struct EmpPlanner EmpPlanner;
+
+/* device < 0: current device.  CUDA is initialised here, not at library load
+ * (the reference calls the planner from a forked child, test_9.py:226-227). */
+int emp_planner_create(EmpPlanner **out, int device, int max_batch, int kmax, int n_enr_max, int max_col);
+void emp_planner_destroy(EmpPlanner *pl);
+
+/* The whole S-L planning step with host buffers: H2D of scenes, both kernels,
+ * D2H of plans (+ rows if not NULL); returns when the host buffers are valid. */
+int emp_sl_plan_host(EmpPlanner *pl, const double *scenes, int batch, const EmpDpParams *dp,
+                     const EmpQpParams *qp, double *plans, int32_t *rows);
+int emp_sl_dp_host(EmpPlanner *pl, const double *scenes, int batch, const EmpDpParams *dp,
+                   double *plans, int32_t *rows);
+int emp_qp_host(EmpPlanner *pl, const double *l_min, const double *l_max, const double *start_l_dl_ddl,
+                int n, int batch, const EmpQpParams *p, double *out_l_dl_ddl, int32_t *status_iters);
+int emp_corridor_host(EmpPlanner *pl, const double *dp_s, const double *dp_l, int n, const double *scenes,
+                      int batch, const EmpQpParams *p, double *lmin_lmax, int32_t *status_iters);
+/* Kernel-only time (ms, CUDA events on the planner's stream) of the last *_host call. */
+double emp_planner_last_kernel_ms(const EmpPlanner *pl);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* EMPLANNER_H_ */

@@ -1,0 +1,155 @@
+"""GPU parity tests for the S-L DP + QP path, called through the C ABI (host-buffer entry points).
+
+Checker = oracle/ (closed-form mode) and tests/golden (outputs of the unmodified reference).
+Tolerances (stated per test):
+  DP   : lattice row indices identical; densified length identical; |dl| <= 1e-12 vs the oracle
+         (bit-for-bit expected: same association order, no FMA); <= 1e-9 m vs the reference on
+         lattice A, <= 1e-4 m on lattices B/C (reference noise of its 6x6 inverse).
+  QP   : per-frame RMS(l_gpu - l_oracle) <= 1e-4 m (north_star) on frames both call optimal;
+         observed ~1e-10.  Iteration counts are compared and reported.
+"""
+import numpy as np
+import pytest
+
+from conftest import lattice_from_golden, load_golden
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def planner():
+    from emplanner_carla_b200 import api
+    pl = api.HostPlanner(max_batch=8192, kmax=8, n_enr_max=64, max_col=64)
+    yield pl
+    pl.close()
+
+
+def _scenes_from(g):
+    from emplanner_carla_b200 import api
+    return api.pack_scenes(g["obs_s"], g["obs_l"], g["nobs"], g["s0"], g["l0"], g["dl0"], g["ddl0"])
+
+
+@pytest.mark.parametrize("tag,tol_ref", [("A", 1e-9), ("B", 1e-4), ("C", 1e-4)])
+def test_dp_matches_reference_golden(planner, tag, tol_ref):
+    from emplanner_carla_b200 import api
+    g = load_golden("sl_%s.npz" % tag)
+    lat = lattice_from_golden(g)
+    dp = api.dp_params(**lat.kwargs())
+    view, rows = planner.dp(_scenes_from(g), dp)
+    n = view.n_enr.astype(int)
+    assert np.array_equal(n, g["ref_n"])
+    has_obs = g["nobs"] > 0
+    assert np.array_equal(rows[has_obs], g["rows"][has_obs])
+    assert np.all(rows[~has_obs] == -1)
+    worst = 0.0
+    for b in range(len(n)):
+        assert np.array_equal(view.enr_s[b, :n[b]], g["ref_s"][b, :n[b]])
+        worst = max(worst, np.abs(view.enr_l[b, :n[b]] - g["ref_l"][b, :n[b]]).max())
+    print("lattice", tag, "max |l_gpu - l_reference| = %.3e" % worst)
+    assert worst <= tol_ref
+
+
+@pytest.mark.parametrize("name", ["A", "B", "C"])
+def test_dp_bit_exact_vs_oracle(planner, name):
+    from emplanner_carla_b200 import api, scenes
+    from oracle import sl_dp
+    lat = scenes.LATTICES[name]
+    B = 256 if name == "A" else 96
+    sc = scenes.sl_scenes(B, lat, 40 + ord(name))
+    dp = api.dp_params(**lat.kwargs())
+    view, rows = planner.dp(api.pack_scenes(**sc), dp)
+    o_rows, o_s, o_l, o_cost = sl_dp.dp_batch(sc["obs_s"], sc["obs_l"], sc["nobs"], sc["s0"], sc["l0"], sc["dl0"],
+                                              sc["ddl0"], **lat.kwargs())
+    assert np.array_equal(rows, o_rows)
+    has = sc["nobs"] > 0
+    assert np.array_equal(view.dp_cost[has], o_cost[has]), "DP cost must be bit-identical to the oracle"
+    for b in range(B):
+        es, el = sl_dp.enrich(o_s[b], o_l[b], sc["s0"][b], sc["l0"][b], sc["dl0"][b], sc["ddl0"][b],
+                              resolution=lat.sampling_res)
+        nb = int(view.n_enr[b])
+        assert nb == len(es)
+        assert np.array_equal(view.enr_s[b, :nb], es)
+        assert np.abs(view.enr_l[b, :nb] - el).max() <= 1e-12
+
+
+@pytest.mark.parametrize("tag", ["A", "B", "C"])
+def test_plan_matches_golden_qp(planner, tag):
+    """Full DP -> [::2] -> corridor -> QP against the golden corridor and QP solution."""
+    from emplanner_carla_b200 import api
+    g = load_golden("sl_%s.npz" % tag)
+    lat = lattice_from_golden(g)
+    dp, qp = api.dp_params(**lat.kwargs()), api.qp_params()
+    view, _ = planner.plan(_scenes_from(g), dp, qp)
+    B = len(g["s0"])
+    st = view.qp_status.astype(int)
+    assert np.array_equal(st == api.QP_CORRIDOR_INDEX, g["cor_index_error"] == 1)
+    opt_ref = g["qp_optimal"] == 1
+    opt_gpu = st == api.QP_OK
+    agree = opt_ref == opt_gpu
+    print("lattice", tag, "status agreement %d/%d" % (agree.sum(), B))
+    assert agree.mean() >= 0.97
+    worst, it_mismatch, cnt = 0.0, 0, 0
+    for b in range(B):
+        if not (opt_ref[b] and opt_gpu[b]):
+            continue
+        n = int(view.n_qp[b])
+        assert n == (g["ref_n"][b] + 1) // 2
+        rms = np.sqrt(np.mean((view.qp_l[b, :n] - g["qp_l"][b, :n]) ** 2))
+        worst = max(worst, rms)
+        it_mismatch += int(view.qp_iters[b] != g["qp_iters"][b])
+        cnt += 1
+    print("lattice", tag, "frames", cnt, "worst RMS l error %.3e" % worst, "iteration mismatches", it_mismatch)
+    assert worst <= 1e-4
+    assert it_mismatch <= max(1, cnt // 20)
+
+
+def test_qp_direct_and_corridor_entry_points(planner):
+    from emplanner_carla_b200 import api
+    g = load_golden("sl_A.npz")
+    ok = (g["cor_index_error"] == 0) & (g["ref_n"] == 48)
+    idx = np.where(ok)[0][:64]
+    n = 24
+    qp = api.qp_params()
+    scenes = _scenes_from(g)[idx]
+    lmin, lmax, stc = planner.corridor(g["ref_s"][idx, 0:48:2], g["ref_l"][idx, 0:48:2], scenes, qp)
+    assert np.all(stc == 0)
+    assert np.array_equal(lmin, g["ref_lmin"][idx, :n]) and np.array_equal(lmax, g["ref_lmax"][idx, :n])
+    start = np.stack([g["l0"][idx], g["dl0"][idx], g["ddl0"][idx]], axis=1)
+    x, st, it = planner.qp(lmin, lmax, start, qp)
+    opt = (g["qp_optimal"][idx] == 1) & (st == 0)
+    assert opt.sum() >= 0.7 * len(idx)
+    err = np.abs(x[opt, 0, :] - g["qp_l"][idx][opt, :n]).max()
+    print("direct QP max |dl| %.3e" % err)
+    assert err <= 1e-4
+
+
+def test_full_size_properties(planner):
+    """BASELINE.json configs[1] at full size (batch 4096, lattice C): size-independent properties."""
+    from emplanner_carla_b200 import api, scenes
+    lat = scenes.LATTICE_C
+    sc = scenes.sl_scenes(4096, lat, 2)
+    dp, qp = api.dp_params(**lat.kwargs()), api.qp_params()
+    rec = api.pack_scenes(**sc)
+    view, rows = planner.plan(rec, dp, qp, want_rows=True)
+    view2, rows2 = planner.plan(rec, dp, qp, want_rows=True)
+    assert np.array_equal(view.raw[:, :7], view2.raw[:, :7]) and np.array_equal(rows, rows2), "run-to-run determinism"
+    n = view.n_enr.astype(int)
+    assert np.all(n == 61)
+    # densified s is strictly increasing and ends at the last lattice column
+    assert np.all(np.diff(view.enr_s[:, :61], axis=1) > 0)
+    assert np.allclose(view.enr_s[:, 60], sc["s0"] + 60 * 1.5, rtol=0, atol=1e-12)
+    # K = 0 frames: straight DP path, QP converges
+    k0 = sc["nobs"] == 0
+    assert np.all(rows[k0] == -1) and np.all(view.enr_l[k0, 1:61] == 0.0)
+    assert np.all(view.qp_status[k0] == 0)
+    # optimal frames satisfy the start pin, the end pin and the corridor box
+    opt = view.qp_status == 0
+    assert opt.mean() > 0.5
+    assert np.abs(view.qp_l[opt, 0] - sc["l0"][opt]).max() < 1e-6
+    assert np.abs(view.qp_l[opt, 30]).max() < 1e-6
+    assert np.all(np.abs(view.qp_l[opt, :31]) <= 10.0 + 1e-6)
+    # permutation equivariance: frames are independent
+    perm = np.random.default_rng(0).permutation(4096)
+    view3, _ = planner.plan(rec[perm], dp, qp)
+    assert np.array_equal(view3.raw[:, :7], view.raw[perm][:, :7])
+    assert np.array_equal(view3.qp_l, view.qp_l[perm])
