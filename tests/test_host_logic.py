@@ -1,0 +1,85 @@
+"""CPU tests of the host-side logic: C-ABI library loads and exports every declared symbol (no compute
+calls without a GPU), record packing, scene generation, the kernel's arithmetic model vs the oracle."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, load_golden
+
+
+def test_library_loads_and_exports_every_declared_symbol():
+    from emplanner_carla_b200 import _lib
+    lib = _lib.lib()                       # must not touch CUDA: works on a box without a GPU
+    hdr = open(os.path.join(ROOT, "include", "emplanner.h")).read()
+    declared = set(re.findall(r"\b(emp_[a-z0-9_]+)\s*\(", hdr))
+    assert declared, "no declarations found"
+    assert declared == set(_lib.exported_symbols()), declared ^ set(_lib.exported_symbols())
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert lib.emp_version() == 100
+    assert lib.emp_scene_stride(8) == 22 and lib.emp_plan_stride(61) == 224
+
+
+def test_param_defaults_match_reference_keyword_defaults():
+    from emplanner_carla_b200 import _lib
+    lib = _lib.lib()
+    d, q = _lib.DpParams(), _lib.QpParams()
+    lib.emp_dp_params_default(ctypes.byref(d))
+    lib.emp_qp_params_default(ctypes.byref(q))
+    py_d, py_q = _lib.dp_params(), _lib.qp_params()
+    for f, _t in _lib.DpParams._fields_:
+        a, b = getattr(d, f), getattr(py_d, f)
+        assert (list(a) == list(b)) if f == "w_smooth" else (a == b), f
+    for f, _t in _lib.QpParams._fields_:
+        assert getattr(q, f) == getattr(py_q, f), f
+    assert (d.row, d.col, d.sample_s, d.sample_l, d.w_collision) == (12, 6, 15, 1.5, 1e12)   # path_planning.py:276-279
+    assert lib.emp_max_enriched(ctypes.byref(d)) == 49
+
+
+def test_argument_errors_are_reported_not_crashed():
+    from emplanner_carla_b200 import _lib
+    lib = _lib.lib()
+    d = _lib.dp_params(row=40)
+    rc = lib.emp_sl_dp_dev(None, 8, 4, ctypes.byref(d), 49, None, None, None)
+    assert rc < 0 and b"row" in lib.emp_last_error()
+    with pytest.raises(_lib.EmpError):
+        _lib.check(rc)
+
+
+def test_pack_scenes_layout_and_scene_prefix_property():
+    from emplanner_carla_b200 import api, scenes
+    a = scenes.sl_scenes(64, scenes.LATTICE_C, 2)
+    b = scenes.sl_scenes(16, scenes.LATTICE_C, 2)
+    for k in a:
+        assert np.array_equal(a[k][:16], b[k], equal_nan=True), k
+    rec = api.pack_scenes(**b)
+    assert rec.shape == (16, 22)
+    assert np.array_equal(rec[:, 0], b["s0"]) and np.array_equal(rec[:, 4], b["nobs"])
+    k = int(b["nobs"][3])
+    assert np.array_equal(rec[3, 6:6 + k], b["obs_s"][3, :k]) and np.array_equal(rec[3, 14:14 + k], b["obs_l"][3, :k])
+    assert np.all(np.isfinite(rec))
+    # obstacle generator keeps cal_lmin_lmax inside the path
+    assert np.nanmax(a["obs_s"]) < scenes.LATTICE_C.horizon - 5
+
+
+@pytest.mark.parametrize("tag", ["A", "C"])
+def test_kernel_arithmetic_model_matches_oracle_qp(tag):
+    """The algorithm the CUDA QP kernel implements (tests/qp_kernel_model.py) reproduces the oracle's
+    coneqp iterates: same status, same iteration count, l within 1e-8 m."""
+    from qp_kernel_model import solve_qp
+    g = load_golden("sl_%s.npz" % tag)
+    worst, n_checked = 0.0, 0
+    for b in range(0, len(g["s0"]), 4):
+        if g["cor_index_error"][b]:
+            continue
+        n = (g["ref_n"][b] + 1) // 2
+        x, status, it = solve_qp(g["ref_lmin"][b, :n], g["ref_lmax"][b, :n], [g["l0"][b], g["dl0"][b], g["ddl0"][b]])
+        assert (status == "optimal") == bool(g["qp_optimal"][b])
+        if status == "optimal":
+            assert it == g["qp_iters"][b]
+            worst = max(worst, np.abs(x[:, 0] - g["qp_l"][b, :n]).max())
+            n_checked += 1
+    assert n_checked >= 8 and worst < 1e-8, worst
