@@ -52,7 +52,7 @@ def qp_flops(n, iters_mean):
 class ClockSampler(threading.Thread):
     """Samples SM clock + throttle reasons during the timed region (B200_PROFILING.md clocks line)."""
 
-    def __init__(self, index=0, period=0.1):
+    def __init__(self, index=0, period=0.01):
         super().__init__(daemon=True)
         self.index, self.period = index, period
         self.samples, self.reasons = [], set()
@@ -296,6 +296,9 @@ def main():
     n_qp = float(view.n_qp.mean())
     iters = float(view.qp_iters.mean())
     frac_opt = float((view.qp_status == 0).mean())
+    it_arr = np.sort(view.qp_iters.astype(int))
+    it_stats = {"p50": int(it_arr[len(it_arr) // 2]), "p99": int(it_arr[int(len(it_arr) * 0.99)]), "max": int(it_arr[-1]),
+                "frames_over_30": int((it_arr > 30).sum())}
     b_dp, b_qp = algorithmic_bytes(n_enr, n_qp)
     peaks = {}
     try:
@@ -332,7 +335,7 @@ def main():
                    "lattice": lat.name, "batch_per_gpu": B, "global_batch": B * world,
                    "parallelism": "frame-sharded x%d" % world,
                    "l2": "flushed with a 256 MiB write between timed steps" if flush is not None else "not flushed",
-                   "qp_optimal_fraction": frac_opt, "qp_mean_iterations": iters},
+                   "qp_optimal_fraction": frac_opt, "qp_mean_iterations": iters, "qp_iterations": it_stats},
         "kernels_ms": {"sl_dp_kernel": t_dp / args.steps, "sl_qp_kernel": t_qp / args.steps,
                        "collective": max(t_all - t_dp - t_qp, 0.0) / args.steps},
         "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",

@@ -35,6 +35,9 @@ def _stale(target, deps):
 
 def build(force=False, verbose=False):
     nvcc = _nvcc()
+    defines = os.environ.get("EMP_DEFINES", "").split()      # tuning experiments, e.g. EMP_DEFINES="-DEMP_QP_MINBLOCKS=3"
+    if defines:
+        force = True
     hdrs = [os.path.join(HERE, f) for f in os.listdir(HERE) if f.endswith((".h", ".cuh"))]
     hdrs.append(os.path.join(os.path.dirname(PKG), "include", "emplanner.h"))
     hdrs.append(os.path.abspath(__file__))
@@ -45,7 +48,7 @@ def build(force=False, verbose=False):
             continue
         obj = os.path.join(HERE, src.replace(".cu", ".o"))
         if force or _stale(obj, [path] + hdrs):
-            cmd = [nvcc] + ARCH + COMMON + extra + (["-Xptxas", "-v"] if verbose else []) + ["-c", path, "-o", obj]
+            cmd = [nvcc] + ARCH + COMMON + extra + defines + (["-Xptxas", "-v"] if verbose else []) + ["-c", path, "-o", obj]
             if verbose:
                 print(" ".join(cmd), flush=True)
             subprocess.run(cmd, check=True)

@@ -9,8 +9,14 @@
 
 namespace emp {
 
-constexpr int DP_WARPS = 8;   // frames (warps) per CTA in the DP kernel
-constexpr int QP_WARPS = 4;   // frames (warps) per CTA in the QP kernel
+#ifndef EMP_DP_WARPS
+#define EMP_DP_WARPS 4
+#endif
+#ifndef EMP_QP_WARPS
+#define EMP_QP_WARPS 4
+#endif
+constexpr int DP_WARPS = EMP_DP_WARPS;   // frames (warps) per CTA in the DP kernel
+constexpr int QP_WARPS = EMP_QP_WARPS;   // frames (warps) per CTA in the QP kernel
 
 struct DpLaunch {
     double res, w_col, w0, w1, w2, w_ref, sample_s, sample_l;

@@ -77,12 +77,16 @@ __device__ __forceinline__ int warp_argmin(double v, int lane) {
 
 struct Factor {                 // per-lane pieces of the KKT factorisation
     double q00, q01, q11, q22;  // Q upper triangular, S_i^-1 = Q Q'
-    double l00, l10, l11, l20, l21, l22;   // Cholesky block L_ii of stage i (pair i,i+1)
+    double l10, l20, l21;       // strict lower part of the Cholesky block L_ii of stage i (pair i,i+1)
     double i00, i11, i22;       // 1 / diag(L_ii)
     double m[9];                // M_i = L_{i-1}^-1 (F X_i E'), row-major
 };
 
-__global__ void __launch_bounds__(QP_WARPS * 32)
+#ifndef EMP_QP_MINBLOCKS
+#define EMP_QP_MINBLOCKS 4
+#endif
+
+__global__ void __launch_bounds__(QP_WARPS * 32, EMP_QP_MINBLOCKS)
 sl_qp_kernel(const double *__restrict__ scenes, double *__restrict__ plans, double *__restrict__ lmin_lmax,
              const double *__restrict__ lmin_in, const double *__restrict__ lmax_in,
              const double *__restrict__ start_in, double *__restrict__ out_x,
@@ -276,7 +280,7 @@ sl_qp_kernel(const double *__restrict__ scenes, double *__restrict__ plans, doub
             const double k20 = e20 + shfl_down(f20, 1);
             const double k21 = e21 + shfl_down(f21, 1);
             const double k22 = (e22 + shfl_down(f22, 1)) + jinv;
-            F.l00 = 1.0; F.l10 = 0.0; F.l11 = 1.0; F.l20 = 0.0; F.l21 = 0.0; F.l22 = 1.0;
+            F.l10 = 0.0; F.l20 = 0.0; F.l21 = 0.0;
             F.i00 = 1.0; F.i11 = 1.0; F.i22 = 1.0;
             EMP_UNROLL
             for (int k = 0; k < 9; ++k) F.m[k] = 0.0;
@@ -285,36 +289,36 @@ sl_qp_kernel(const double *__restrict__ scenes, double *__restrict__ plans, doub
                 const int src = i > 0 ? i - 1 : 0;
                 const double pl10 = shfl(F.l10, src), pl20 = shfl(F.l20, src), pl21 = shfl(F.l21, src);
                 const double pi00 = shfl(F.i00, src), pi11 = shfl(F.i11, src), pi22 = shfl(F.i22, src);
-                double M[9];
-                EMP_UNROLL
-                for (int c = 0; c < 3; ++c) {                     // M = L_{i-1}^-1 B, column c
-                    const double m0 = B[c] * pi00;
-                    const double m1 = (B[3 + c] - pl10 * m0) * pi11;
-                    const double m2 = ((B[6 + c] - pl20 * m0) - pl21 * m1) * pi22;
-                    M[c] = i > 0 ? m0 : 0.0;
-                    M[3 + c] = i > 0 ? m1 : 0.0;
-                    M[6 + c] = i > 0 ? m2 : 0.0;
-                }
-                // D = K_ii - M'M
-                const double d00 = k00 - (M[0] * M[0] + M[3] * M[3] + M[6] * M[6]);
-                const double d10 = k10 - (M[1] * M[0] + M[4] * M[3] + M[7] * M[6]);
-                const double d11 = k11 - (M[1] * M[1] + M[4] * M[4] + M[7] * M[7]);
-                const double d20 = k20 - (M[2] * M[0] + M[5] * M[3] + M[8] * M[6]);
-                const double d21 = k21 - (M[2] * M[1] + M[5] * M[4] + M[8] * M[7]);
-                const double d22 = k22 - (M[2] * M[2] + M[5] * M[5] + M[8] * M[8]);
-                const double j00 = rsqrt(d00);
-                const double c10 = d10 * j00, c20 = d20 * j00;
-                const double t11 = d11 - c10 * c10;
-                const double j11 = rsqrt(t11);
-                const double c21 = (d21 - c20 * c10) * j11;
-                const double t22 = (d22 - c20 * c20) - c21 * c21;
-                const double j22 = rsqrt(t22);
-                if (lane == i) {
+                if (lane == i) {                                  // only the owner of stage i works
+                    if (i > 0) {
+                        EMP_UNROLL
+                        for (int c = 0; c < 3; ++c) {             // M = L_{i-1}^-1 B, column c
+                            const double m0 = B[c] * pi00;
+                            const double m1 = (B[3 + c] - pl10 * m0) * pi11;
+                            const double m2 = ((B[6 + c] - pl20 * m0) - pl21 * m1) * pi22;
+                            F.m[c] = m0;
+                            F.m[3 + c] = m1;
+                            F.m[6 + c] = m2;
+                        }
+                    }
+                    const double *M = F.m;
+                    // D = K_ii - M'M
+                    const double d00 = k00 - (M[0] * M[0] + M[3] * M[3] + M[6] * M[6]);
+                    const double d10 = k10 - (M[1] * M[0] + M[4] * M[3] + M[7] * M[6]);
+                    const double d11 = k11 - (M[1] * M[1] + M[4] * M[4] + M[7] * M[7]);
+                    const double d20 = k20 - (M[2] * M[0] + M[5] * M[3] + M[8] * M[6]);
+                    const double d21 = k21 - (M[2] * M[1] + M[5] * M[4] + M[8] * M[7]);
+                    const double d22 = k22 - (M[2] * M[2] + M[5] * M[5] + M[8] * M[8]);
+                    const double j00 = rsqrt(d00);
+                    const double c10 = d10 * j00, c20 = d20 * j00;
+                    const double t11 = d11 - c10 * c10;
+                    const double j11 = rsqrt(t11);
+                    const double c21 = (d21 - c20 * c10) * j11;
+                    const double t22 = (d22 - c20 * c20) - c21 * c21;
+                    const double j22 = rsqrt(t22);
                     bad = !(d00 > 0.0) || !(t11 > 0.0) || !(t22 > 0.0) || !isfinite(j00 + j11 + j22);
-                    F.l00 = d00 * j00; F.l10 = c10; F.l11 = t11 * j11; F.l20 = c20; F.l21 = c21; F.l22 = t22 * j22;
+                    F.l10 = c10; F.l20 = c20; F.l21 = c21;
                     F.i00 = j00; F.i11 = j11; F.i22 = j22;
-                    EMP_UNROLL
-                    for (int k = 0; k < 9; ++k) F.m[k] = M[k];
                 }
             }
             broke = __any_sync(EMP_FULL_MASK, bad);
@@ -344,31 +348,29 @@ sl_qp_kernel(const double *__restrict__ scenes, double *__restrict__ plans, doub
             double t0 = 0.0, t1 = 0.0, t2 = 0.0;
             for (int i = 0; i < n - 1; ++i) {
                 const int src = i > 0 ? i - 1 : 0;
-                double p0 = shfl(t0, src), p1 = shfl(t1, src), p2 = shfl(t2, src);
-                if (i == 0) { p0 = 0.0; p1 = 0.0; p2 = 0.0; }
-                const double rr0 = r0 - ((F.m[0] * p0 + F.m[3] * p1) + F.m[6] * p2);
-                const double rr1 = r1 - ((F.m[1] * p0 + F.m[4] * p1) + F.m[7] * p2);
-                const double rr2 = r2 - ((F.m[2] * p0 + F.m[5] * p1) + F.m[8] * p2);
-                const double c0 = rr0 * F.i00;
-                const double c1 = (rr1 - F.l10 * c0) * F.i11;
-                const double c2 = ((rr2 - F.l20 * c0) - F.l21 * c1) * F.i22;
-                if (lane == i) { t0 = c0; t1 = c1; t2 = c2; }
+                const double p0 = shfl(t0, src), p1 = shfl(t1, src), p2 = shfl(t2, src);
+                if (lane == i) {
+                    const double rr0 = r0 - ((F.m[0] * p0 + F.m[3] * p1) + F.m[6] * p2);
+                    const double rr1 = r1 - ((F.m[1] * p0 + F.m[4] * p1) + F.m[7] * p2);
+                    const double rr2 = r2 - ((F.m[2] * p0 + F.m[5] * p1) + F.m[8] * p2);
+                    t0 = rr0 * F.i00;
+                    t1 = (rr1 - F.l10 * t0) * F.i11;
+                    t2 = ((rr2 - F.l20 * t0) - F.l21 * t1) * F.i22;
+                }
             }
             // backward substitution chain  y_i = L_ii^-T (t_i - M_{i+1} y_{i+1})
             double y0 = 0.0, y1 = 0.0, y2 = 0.0, cd0 = 0.0, cd1 = 0.0, cd2 = 0.0;
             for (int i = n - 2; i >= 0; --i) {
                 const int src = i + 1;
-                double u0 = shfl(cd0, src), u1 = shfl(cd1, src), u2 = shfl(cd2, src);
-                if (i == n - 2) { u0 = 0.0; u1 = 0.0; u2 = 0.0; }
-                const double rr0 = t0 - u0, rr1 = t1 - u1, rr2 = t2 - u2;
-                const double c2 = rr2 * F.i22;
-                const double c1 = (rr1 - F.l21 * c2) * F.i11;
-                const double c0 = ((rr0 - F.l10 * c1) - F.l20 * c2) * F.i00;
+                const double u0 = shfl(cd0, src), u1 = shfl(cd1, src), u2 = shfl(cd2, src);
                 if (lane == i) {
-                    y0 = c0; y1 = c1; y2 = c2;
-                    cd0 = (F.m[0] * c0 + F.m[1] * c1) + F.m[2] * c2;
-                    cd1 = (F.m[3] * c0 + F.m[4] * c1) + F.m[5] * c2;
-                    cd2 = (F.m[6] * c0 + F.m[7] * c1) + F.m[8] * c2;
+                    const double rr0 = t0 - u0, rr1 = t1 - u1, rr2 = t2 - u2;
+                    y2 = rr2 * F.i22;
+                    y1 = (rr1 - F.l21 * y2) * F.i11;
+                    y0 = ((rr0 - F.l10 * y1) - F.l20 * y2) * F.i00;
+                    cd0 = (F.m[0] * y0 + F.m[1] * y1) + F.m[2] * y2;
+                    cd1 = (F.m[3] * y0 + F.m[4] * y1) + F.m[5] * y2;
+                    cd2 = (F.m[6] * y0 + F.m[7] * y1) + F.m[8] * y2;
                 }
             }
             if (!stage) { y0 = 0.0; y1 = 0.0; y2 = 0.0; }
@@ -458,6 +460,7 @@ sl_qp_kernel(const double *__restrict__ scenes, double *__restrict__ plans, doub
         const double resy0 = 1.0;                                  // b = 0
         const double resz0 = fmax(1.0, sqrt(n0[1]));
         if (broke) qp_status = EMP_QP_UNKNOWN_NUMERIC;             // cvxopt raises ValueError here
+        const double gap_limit = 100.0 * gap;                      // see "divergence exit" below
 
         // ---------------- main loop ----------------------------------------------
         double ws3[NR];
@@ -500,11 +503,16 @@ sl_qp_kernel(const double *__restrict__ scenes, double *__restrict__ plans, doub
             if (pres <= Q.feastol && dres <= Q.feastol && (gap <= Q.abstol || (have_rel && relgap <= Q.reltol))) break;
             if (iters == Q.maxiters) { qp_status = EMP_QP_UNKNOWN_MAXITER; break; }
             if (!isfinite((gap + resx) + resz)) { qp_status = EMP_QP_UNKNOWN_NUMERIC; break; }
+            // Divergence exit: on an infeasible corridor coneqp has no certificate; cvxopt iterates until its
+            // Cholesky breaks down or maxiters and reports 'unknown'.  The gap of a converging solve never grows
+            // above its initial value, so a gap 100x the initial one ends the solve with the same 'unknown'.
+            if (iters > 0 && gap > gap_limit) { qp_status = EMP_QP_UNKNOWN_NUMERIC; break; }
 
-            double is[NR], w[NR];
+            double is[NR], iz[NR], w[NR];
             EMP_UNROLL
             for (int r = 0; r < NR; ++r) {
                 is[r] = 1.0 / s[r];
+                iz[r] = 1.0 / z[r];
                 w[r] = z[r] * is[r];
             }
             factor(w);
@@ -538,7 +546,7 @@ sl_qp_kernel(const double *__restrict__ scenes, double *__restrict__ plans, doub
                     if (valid) {
                         dsdz += dsv[r] * dz[r];
                         ts = fmax(ts, -dsv[r] * is[r]);
-                        tz = fmax(tz, -dz[r] / z[r]);
+                        tz = fmax(tz, -dz[r] * iz[r]);
                     }
                     if (pass == 0) ws3[r] = dsv[r] * dz[r];
                 }

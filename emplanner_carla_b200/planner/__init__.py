@@ -1,0 +1,16 @@
+"""Drop-in replacement for the reference's `planner` package (6Lackiu/EMplanner_Carla @ 1f115a5).
+
+Put the directory that contains this package (`emplanner_carla_b200/`) in front of the reference
+root on sys.path and the driver scripts' `from planner import planning_utils, path_planning`
+(test_9.py:26) resolves here: same module names, function names, argument order and defaults,
+list-in/list-out types - with the arithmetic running in libemplanner.so on the GPU.
+See INTEGRATION.md.
+"""
+import os as _os
+import sys as _sys
+
+try:
+    import emplanner_carla_b200 as _pkg  # noqa: F401
+except ImportError:  # imported as top-level `planner`: make the parent package importable
+    _sys.path.append(_os.path.dirname(_os.path.dirname(_os.path.dirname(_os.path.abspath(__file__)))))
+    import emplanner_carla_b200 as _pkg  # noqa: F401

@@ -1,0 +1,88 @@
+"""GPU tests of the drop-in `planner` package: the reference's own call sequence (test_9.py:180-201)
+with the reference's function names, against golden outputs of the unmodified reference."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, load_golden
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def planner_pkg():
+    pkg_dir = os.path.join(ROOT, "emplanner_carla_b200")
+    sys.path.insert(0, pkg_dir)
+    for k in [k for k in sys.modules if k == "planner" or k.startswith("planner.")]:
+        del sys.modules[k]
+    from planner import path_planning      # exactly the reference's import line (test_9.py:26)
+    yield path_planning
+    sys.path.remove(pkg_dir)
+    for k in [k for k in sys.modules if k == "planner" or k.startswith("planner.")]:
+        del sys.modules[k]
+
+
+def test_reference_call_sequence_lattice_a(planner_pkg):
+    pp = planner_pkg
+    g = load_golden("sl_A.npz")
+    done = 0
+    for b in range(0, 40):
+        K = int(g["nobs"][b])
+        obs_s, obs_l = list(g["obs_s"][b, :K]), list(g["obs_l"][b, :K])
+        dp_s, dp_l = pp.DP_algorithm(obs_s, obs_l, plan_start_s=g["s0"][b], plan_start_l=g["l0"][b],
+                                     plan_start_dl=g["dl0"][b], plan_start_ddl=g["ddl0"][b])
+        n = g["ref_n"][b]
+        assert isinstance(dp_s, list) and len(dp_s) == n
+        assert np.array_equal(dp_s, g["ref_s"][b, :n]) and np.abs(np.array(dp_l) - g["ref_l"][b, :n]).max() < 1e-9
+        dp_l2, dp_s2 = dp_l[::2], dp_s[::2]
+        if g["cor_index_error"][b]:
+            with pytest.raises(IndexError):
+                pp.cal_lmin_lmax(dp_path_s=dp_s2, dp_path_l=dp_l2, obs_s_list=obs_s, obs_l_list=obs_l,
+                                 obs_length=5, obs_width=5)
+            continue
+        l_min, l_max = pp.cal_lmin_lmax(dp_path_s=dp_s2, dp_path_l=dp_l2, obs_s_list=obs_s, obs_l_list=obs_l,
+                                        obs_length=5, obs_width=5)
+        m = len(l_min)
+        assert np.array_equal(l_min, g["ref_lmin"][b, :m]) and np.array_equal(l_max, g["ref_lmax"][b, :m])
+        ql, qdl, qddl = pp.Quadratic_planning(l_min, l_max, plan_start_l=g["l0"][b], plan_start_dl=g["dl0"][b],
+                                              plan_start_ddl=g["ddl0"][b])
+        assert isinstance(ql, list) and len(ql) == m == len(qdl) == len(qddl)
+        if g["qp_optimal"][b] and pp.Quadratic_planning.last_status[0] == 0:
+            assert np.sqrt(np.mean((np.array(ql) - g["qp_l"][b, :m]) ** 2)) < 1e-4
+            assert np.abs(np.array(qdl) - g["qp_dl"][b, :m]).max() < 1e-4
+            done += 1
+    assert done >= 20
+
+
+def test_non_default_parameters_against_oracle(planner_pkg):
+    from oracle import sl_dp, sl_qp
+    pp = planner_pkg
+    kw = dict(sampling_res=1, w_collision_cost=1e10, w_smooth_cost=[100, 2000, 3000], w_reference_cost=35,
+              row=9, col=8, sample_s=10, sample_l=1.0)
+    obs_s, obs_l = [18.0, 40.5, 66.0], [0.4, -1.1, 1.9]
+    s, l = pp.DP_algorithm(obs_s, obs_l, 1.3, 0.2, 0.01, -0.004, **kw)
+    so, lo, _ = sl_dp.dp_algorithm(obs_s, obs_l, 1.3, 0.2, 0.01, -0.004, **kw)
+    assert len(s) == len(so) and np.array_equal(s, so) and np.abs(np.array(l) - lo).max() < 1e-12
+    lmin = np.linspace(-10, -8, 17)
+    lmax = np.linspace(9, 10, 17)
+    qkw = dict(dp_sampling_res=1, w_cost_l=700, w_cost_dl=11, w_cost_ddl=1300, w_cost_dddl=170, w_cost_centre=190,
+               w_cost_end_l=23, w_cost_end_dl=29, w_cost_end_ddl=31, host_d1=2.5, host_d2=1.2, host_w=2)
+    ql, qdl, qddl = pp.Quadratic_planning(lmin, lmax, 0.3, 0.01, -0.02, **qkw)
+    ol, odl, oddl, info = sl_qp.quadratic_planning(lmin, lmax, 0.3, 0.01, -0.02, **qkw)
+    assert info["status"] == "optimal" and pp.Quadratic_planning.last_status == (0, info["iterations"])
+    assert np.abs(np.array(ql) - ol).max() < 1e-6 and np.abs(np.array(qddl) - oddl).max() < 1e-6
+
+
+def test_more_than_eight_obstacles_and_empty_list(planner_pkg):
+    from oracle import sl_dp
+    pp = planner_pkg
+    rng = np.random.default_rng(4)
+    obs_s = sorted(rng.uniform(8, 80, 11))
+    obs_l = list(rng.uniform(-3, 3, 11))
+    s, l = pp.DP_algorithm(obs_s, obs_l, 0.7, -0.1, 0.0, 0.0)
+    so, lo, _ = sl_dp.dp_algorithm(obs_s, obs_l, 0.7, -0.1, 0.0, 0.0)
+    assert np.array_equal(s, so) and np.abs(np.array(l) - lo).max() < 1e-12
+    s, l = pp.DP_algorithm([], [], 0.7, -0.1, 0.0, 0.0)        # no obstacle: straight branch (:362-363)
+    assert all(v == 0.0 for v in l[8:])
