@@ -48,7 +48,7 @@ int make_dp_launch(emp::DpLaunch &L, const EmpDpParams *p, int kmax, int batch, 
     const int RR = L.R * L.R;
     int off = 16;                                        // mbarrier
     L.off_slab = off;  off += align_up(emp::DP_WARPS * L.scene_stride * 8, 16);
-    L.off_f0 = off;    off += align_up(EMP_NSAMPLE * 8, 16);
+    L.off_f0 = off;    off += align_up(2 * EMP_NSAMPLE * 8, 16);       // f0[10] + um[10]
     L.off_nl = off;    off += EMP_MAX_ROW * 8;
     L.off_refc = off;  off += align_up(RR * 8, 16);
     L.off_warp = off;
