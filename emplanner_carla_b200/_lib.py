@@ -43,6 +43,10 @@ _SIGNATURES = {
     "emp_qp_dev": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, _QPP, _P, _P, _P]),
     "emp_corridor_dev": (C.c_int, [_P, _P, C.c_int, _P, C.c_int, C.c_int, _QPP, _P, _P, _P]),
     "emp_sl_plan_dev": (C.c_int, [_P, C.c_int, C.c_int, _DPP, _QPP, C.c_int, _P, _P, _P]),
+    "emp_frenet_project_dev": (C.c_int, [_P, C.c_int, _P, _P, _P, C.c_int, _P, _P, _P, _P, C.c_int, _P, _P, _P, _P, _P, _P]),
+    "emp_frenet_to_cart_dev": (C.c_int, [_P, _P, C.c_int, _P, _P, _P, _P, C.c_int, C.c_int, _P, _P, _P]),
+    "emp_frenet_project_host": (C.c_int, [_P, _P, C.c_int, _P, _P, _P, C.c_int, _P, _P, _P, _P, C.c_int, _P, _P, _P, _P, _P]),
+    "emp_frenet_to_cart_host": (C.c_int, [_P, _P, _P, C.c_int, _P, _P, _P, _P, C.c_int, C.c_int, _P, _P]),
     "emp_fp64_peak": (C.c_int, [C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "emp_planner_create": (C.c_int, [C.POINTER(_P), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),
     "emp_planner_destroy": (None, [_P]),

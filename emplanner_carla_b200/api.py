@@ -167,6 +167,51 @@ class HostPlanner:
                                                 _ptr(out), _ptr(si)))
         return out[:, 0].copy(), out[:, 1].copy(), si[:, 0].copy()
 
+    # ---- Cartesian <-> Frenet (K4) ---------------------------------------------------------
+    def frenet_project(self, lines, origin=None, points=None, npts=None, vel=None, acc=None, s_map_in=None,
+                       pre_match=None, want=("s_map", "match", "sl")):
+        """cal_s_map_fun / cal_s_l_fun / cal_s_l_deri_fun / match_projection_points / find_match_points for a
+        batch of scenes.  lines [B,N,4]; origin [B,2]; points/vel/acc [B,P,2].  Returns a dict with the
+        requested outputs among s_map [B,N], match [B,P], proj [B,P,4], sl [B,P,2], deriv [B,P,7]."""
+        f64 = lambda a: None if a is None else np.ascontiguousarray(a, dtype=np.float64)
+        i32 = lambda a: None if a is None else np.ascontiguousarray(a, dtype=np.int32)
+        lines, origin, points, vel, acc, s_map_in = [f64(a) for a in (lines, origin, points, vel, acc, s_map_in)]
+        npts, pre_match = i32(npts), i32(pre_match)
+        B, N = lines.shape[0], lines.shape[1]
+        P = points.shape[1] if points is not None else 0
+        out = {}
+        if "s_map" in want and origin is not None:
+            out["s_map"] = np.zeros((B, N))
+        if points is not None:
+            if "match" in want:
+                out["match"] = np.zeros((B, P), dtype=np.int32)
+            if "proj" in want:
+                out["proj"] = np.zeros((B, P, 4))
+            if "sl" in want:
+                out["sl"] = np.zeros((B, P, 2))
+            if "deriv" in want:
+                out["deriv"] = np.zeros((B, P, 7))
+        g = lambda k: _ptr(out[k]) if k in out else None
+        o = lambda a: _ptr(a) if a is not None else None
+        _lib.check(_lib.lib().emp_frenet_project_host(self._h, _ptr(lines), N, o(origin), o(points), o(npts), max(P, 1),
+                                                      o(vel), o(acc), o(s_map_in), o(pre_match), B, g("s_map"),
+                                                      g("match"), g("proj"), g("sl"), g("deriv")))
+        return out
+
+    def frenet_to_cart(self, lines, s_map, start_sl, path_s, path_l, npath=None):
+        """frenet_2_x_y_theta_kappa without the trailing smoother.  Returns (cart [B,M+1,4], ncart [B])."""
+        f64 = lambda a: np.ascontiguousarray(a, dtype=np.float64)
+        lines, s_map, start_sl, path_s, path_l = [f64(a) for a in (lines, s_map, start_sl, path_s, path_l)]
+        B, N = lines.shape[0], lines.shape[1]
+        M = path_s.shape[1]
+        npath = None if npath is None else np.ascontiguousarray(npath, dtype=np.int32)
+        cart = np.zeros((B, M + 1, 4))
+        ncart = np.zeros(B, dtype=np.int32)
+        _lib.check(_lib.lib().emp_frenet_to_cart_host(self._h, _ptr(lines), _ptr(s_map), N, _ptr(start_sl), _ptr(path_s),
+                                                      _ptr(path_l), _ptr(npath) if npath is not None else None, M, B,
+                                                      _ptr(cart), _ptr(ncart)))
+        return cart, ncart
+
     @property
     def last_kernel_ms(self):
         return _lib.lib().emp_planner_last_kernel_ms(self._h)

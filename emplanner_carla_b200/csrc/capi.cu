@@ -7,6 +7,7 @@
 #include <new>
 #include "emp_common.cuh"
 #include "sl_kernels.h"
+#include "frenet_kernels.h"
 
 namespace {
 
@@ -79,6 +80,33 @@ int make_qp_launch(emp::QpLaunch &L, const EmpQpParams *p, int kmax, int batch, 
     return 0;
 }
 
+}  // namespace
+
+namespace {
+// Temporary device buffers for the host-buffer Frenet entry points (stream-ordered allocation).
+struct Tmp {
+    cudaStream_t st;
+    void *ptrs[16];
+    int n = 0;
+    cudaError_t err = cudaSuccess;
+    explicit Tmp(cudaStream_t s) : st(s) {}
+    ~Tmp() { for (int i = 0; i < n; ++i) cudaFreeAsync(ptrs[i], st); }
+    template <typename T> T *in(const T *host, size_t count) {
+        if (!host || count == 0) return nullptr;
+        T *d = out<T>(count);
+        if (d && err == cudaSuccess) err = cudaMemcpyAsync(d, host, count * sizeof(T), cudaMemcpyHostToDevice, st);
+        return d;
+    }
+    template <typename T> T *out(size_t count) {
+        void *d = nullptr;
+        if (err == cudaSuccess) err = cudaMallocAsync(&d, count * sizeof(T), st);
+        if (d) ptrs[n++] = d;
+        return (T *)d;
+    }
+    template <typename T> void back(T *host, const T *dev, size_t count) {
+        if (host && dev && err == cudaSuccess) err = cudaMemcpyAsync(host, dev, count * sizeof(T), cudaMemcpyDeviceToHost, st);
+    }
+};
 }  // namespace
 
 struct EmpPlanner {
@@ -174,6 +202,35 @@ int emp_sl_plan_dev(const double *scenes, int kmax, int batch, const EmpDpParams
                     int n_enr_max, double *plans, int32_t *rows, void *stream) {
     if (int rc = emp_sl_dp_dev(scenes, kmax, batch, dp, n_enr_max, plans, rows, stream)) return rc;
     return emp_sl_qp_dev(scenes, kmax, batch, qp, n_enr_max, plans, nullptr, stream);
+}
+
+int emp_frenet_project_dev(const double *lines, int n_nodes, const double *origin, const double *points,
+                           const int32_t *npts, int max_points, const double *vel, const double *acc,
+                           const double *s_map_in, const int32_t *pre_match, int batch,
+                           double *s_map, int32_t *match, double *proj, double *sl, double *deriv, void *stream) {
+    if (batch < 0 || n_nodes < 2 || n_nodes > 1024) return fail(-2, "bad batch / n_nodes (2..1024)");
+    if (batch == 0) return 0;
+    if (!lines) return fail(-1, "lines is NULL");
+    if (deriv && (!vel || !acc || !points || !origin)) return fail(-1, "deriv needs points, vel, acc and origin");
+    if (sl && !origin && !s_map_in) return fail(-1, "sl needs origin or s_map_in");
+    if (points && max_points < 1) return fail(-2, "max_points must be >= 1");
+    emp::FrenetLaunch L{batch, n_nodes, max_points};
+    if (16 + (size_t)emp::FR_WARPS * 5 * n_nodes * 8 > 227u * 1024u) return fail(-3, "reference line too long for shared memory");
+    cudaError_t e = emp::launch_frenet_project(lines, origin, points, npts, vel, acc, s_map_in, pre_match, proj, s_map, match, sl, deriv, L,
+                                               (cudaStream_t)stream);
+    return e == cudaSuccess ? 0 : fail_cuda(e, "frenet_project launch");
+}
+
+int emp_frenet_to_cart_dev(const double *lines, const double *s_map, int n_nodes, const double *start_sl,
+                           const double *path_s, const double *path_l, const int32_t *npath, int max_points,
+                           int batch, double *cart, int32_t *ncart, void *stream) {
+    if (batch < 0 || n_nodes < 2 || max_points < 1) return fail(-2, "bad batch / n_nodes / max_points");
+    if (batch == 0) return 0;
+    if (!lines || !s_map || !start_sl || !path_s || !path_l || !cart || !ncart) return fail(-1, "NULL argument");
+    emp::FrenetLaunch L{batch, n_nodes, max_points};
+    cudaError_t e = emp::launch_frenet_to_cart(lines, s_map, start_sl, path_s, path_l, npath, cart, ncart, L,
+                                               (cudaStream_t)stream);
+    return e == cudaSuccess ? 0 : fail_cuda(e, "frenet_to_cart launch");
 }
 
 int emp_fp64_peak(int iters, double *tflops, double *ms) {
@@ -328,6 +385,71 @@ int emp_corridor_host(EmpPlanner *pl, const double *dp_s, const double *dp_l, in
     EMP_CK(cudaMemcpyAsync(status_iters, pl->d_status, (size_t)batch * 2 * 4, cudaMemcpyDeviceToHost, pl->stream), "D2H status");
     EMP_CK(cudaStreamSynchronize(pl->stream), "planner stream");
     return 0;
+}
+
+int emp_frenet_project_host(EmpPlanner *pl, const double *lines, int n_nodes, const double *origin,
+                            const double *points, const int32_t *npts, int max_points, const double *vel,
+                            const double *acc, const double *s_map_in, const int32_t *pre_match, int batch,
+                            double *s_map, int32_t *match, double *proj, double *sl, double *deriv) {
+    if (!pl) return fail(-1, "planner is NULL");
+    if (batch <= 0) return batch == 0 ? 0 : fail(-2, "bad batch");
+    EMP_CK(cudaSetDevice(pl->device), "cudaSetDevice");
+    const size_t B = batch, P = points ? max_points : 0;
+    int rc;
+    {
+        Tmp t(pl->stream);
+        const double *d_lines = t.in(lines, B * n_nodes * 4), *d_org = t.in(origin, B * 2);
+        const double *d_pts = t.in(points, B * P * 2), *d_vel = t.in(vel, B * P * 2), *d_acc = t.in(acc, B * P * 2);
+        const int32_t *d_np = t.in(npts, B), *d_pre = t.in(pre_match, B);
+        const double *d_smin = t.in(s_map_in, B * n_nodes);
+        double *d_smap = s_map ? t.out<double>(B * n_nodes) : nullptr;
+        double *d_proj = (proj && P) ? t.out<double>(B * P * 4) : nullptr;
+        int32_t *d_match = (match && P) ? t.out<int32_t>(B * P) : nullptr;
+        double *d_sl = (sl && P) ? t.out<double>(B * P * 2) : nullptr;
+        double *d_der = (deriv && P) ? t.out<double>(B * P * 7) : nullptr;
+        if (t.err != cudaSuccess) return fail_cuda(t.err, "frenet_project_host staging");
+        rc = emp_frenet_project_dev(d_lines, n_nodes, d_org, d_pts, d_np, max_points, d_vel, d_acc, d_smin, d_pre,
+                                    batch, d_smap, d_match, d_proj, d_sl, d_der, pl->stream);
+        if (rc == 0) {
+            t.back(s_map, d_smap, B * n_nodes);
+            t.back(match, d_match, B * P);
+            t.back(proj, d_proj, B * P * 4);
+            t.back(sl, d_sl, B * P * 2);
+            t.back(deriv, d_der, B * P * 7);
+            if (t.err != cudaSuccess) return fail_cuda(t.err, "frenet_project_host copy-back");
+        }
+    }
+    EMP_CK(cudaStreamSynchronize(pl->stream), "planner stream");
+    return rc;
+}
+
+int emp_frenet_to_cart_host(EmpPlanner *pl, const double *lines, const double *s_map, int n_nodes,
+                            const double *start_sl, const double *path_s, const double *path_l,
+                            const int32_t *npath, int max_points, int batch, double *cart, int32_t *ncart) {
+    if (!pl || !cart || !ncart) return fail(-1, "NULL argument");
+    if (batch <= 0) return batch == 0 ? 0 : fail(-2, "bad batch");
+    EMP_CK(cudaSetDevice(pl->device), "cudaSetDevice");
+    const size_t B = batch, M = max_points;
+    int rc;
+    {
+        Tmp t(pl->stream);
+        const double *d_lines = t.in(lines, B * n_nodes * 4), *d_smap = t.in(s_map, B * n_nodes);
+        const double *d_start = t.in(start_sl, B * 2), *d_ps = t.in(path_s, B * M), *d_pl = t.in(path_l, B * M);
+        const int32_t *d_np = t.in(npath, B);
+        double *d_cart = t.out<double>(B * (M + 1) * 4);
+        int32_t *d_nc = t.out<int32_t>(B);
+        if (t.err != cudaSuccess) return fail_cuda(t.err, "frenet_to_cart_host staging");
+        cudaMemsetAsync(d_cart, 0xff, B * (M + 1) * 4 * sizeof(double), pl->stream);     // unwritten rows read as NaN
+        rc = emp_frenet_to_cart_dev(d_lines, d_smap, n_nodes, d_start, d_ps, d_pl, d_np, max_points, batch, d_cart,
+                                    d_nc, pl->stream);
+        if (rc == 0) {
+            t.back(cart, d_cart, B * (M + 1) * 4);
+            t.back(ncart, d_nc, B);
+            if (t.err != cudaSuccess) return fail_cuda(t.err, "frenet_to_cart_host copy-back");
+        }
+    }
+    EMP_CK(cudaStreamSynchronize(pl->stream), "planner stream");
+    return rc;
 }
 
 double emp_planner_last_kernel_ms(const EmpPlanner *pl) { return pl ? (double)pl->last_ms : 0.0; }

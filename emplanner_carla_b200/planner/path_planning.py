@@ -71,3 +71,45 @@ def Quadratic_planning(l_min, l_max, plan_start_l, plan_start_dl, plan_start_ddl
 
 
 Quadratic_planning.last_status = None
+
+
+def cal_proj_point(s, pre_match_index, frenet_path_opt: list, s_map: list):
+    """Projection of arc length s on the reference line (reference :52-75).  Returns
+    (proj_x, proj_y, proj_theta, proj_kappa, match_index); raises IndexError beyond the map like the
+    reference's unguarded walk (:63)."""
+    line = np.asarray([tuple(p)[:4] for p in frenet_path_opt], dtype=np.float64)
+    smap = np.asarray(s_map, dtype=np.float64)
+    # the walk never moves backwards: start it at pre_match_index by hiding the nodes before it
+    k = int(pre_match_index)
+    cart, ncart = _runtime.planner().frenet_to_cart(line[None, k:], smap[None, k:], np.array([[s, 0.0]]),
+                                                    np.array([[s]]), np.array([[0.0]]))
+    if ncart[0] < 0 or len(smap) - k < 2:
+        raise IndexError("list index out of range")
+    if ncart[0] >= 2:
+        x, y, th, kap = cart[0, 1]
+        # recover the node index from theta = theta_m + kappa_m * (s - s_map[m]) is ambiguous; use the s-map
+        m = k
+        while m + 1 < len(smap) - 1 and smap[m + 1] < s:
+            m += 1
+        return x, y, th, kap, m
+    raise IndexError("list index out of range")
+
+
+def frenet_2_x_y_theta_kappa(plan_start_s, plan_start_l, enriched_s_list: list, enriched_l_list: list,
+                             frenet_path_opt: list, s_map: list, smooth=True):
+    """(s, l) path -> Cartesian [(x, y, theta, kappa), ...] (reference :15-49): projection on the GPU
+    (truncated where s > s_map[-1], :40-41), then planning_utils.smooth_reference_line like the reference (:47)."""
+    line = np.asarray([tuple(p)[:4] for p in frenet_path_opt], dtype=np.float64)[None]
+    smap = np.asarray(s_map, dtype=np.float64)[None]
+    ps = np.asarray(enriched_s_list, dtype=np.float64)[None]
+    pl_ = np.asarray(enriched_l_list, dtype=np.float64)[None]
+    cart, ncart = _runtime.planner().frenet_to_cart(line, smap, np.array([[plan_start_s, plan_start_l]]), ps, pl_)
+    if ncart[0] < 0:
+        raise IndexError("list index out of range")
+    n = int(ncart[0])
+    target_xy = [(cart[0, 0, 0], cart[0, 0, 1])] + [tuple(cart[0, i]) for i in range(1, n)]
+    if not smooth:
+        return target_xy
+    from . import planning_utils
+    return planning_utils.smooth_reference_line(target_xy)
+

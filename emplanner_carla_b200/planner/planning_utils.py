@@ -1,0 +1,83 @@
+"""GPU drop-in for the reference's planner/planning_utils.py (same names, arguments, defaults, return types).
+
+The Cartesian<->Frenet arithmetic runs in libemplanner.so (csrc/frenet.cu) through
+emplanner_carla_b200.api.HostPlanner; `sampling` is pure list slicing and stays in Python.
+Reference line numbers cite planning_utils.py @ 1f115a5.  Not provided: the three CARLA-actor helpers
+(Vector_fun, waypoint_list_2_target_path, predict_block*), which need live simulator actors.
+"""
+import numpy as np
+
+from . import _runtime
+
+
+def _line(path):
+    a = np.asarray([tuple(p)[:4] for p in path], dtype=np.float64)
+    if a.ndim != 2 or a.shape[1] != 4:
+        raise ValueError("reference line must be [(x, y, theta, kappa), ...]")
+    return a[None]
+
+
+def _pts(xy_list):
+    return np.asarray([(p[0], p[1]) for p in xy_list], dtype=np.float64)[None]
+
+
+def match_projection_points(xy_list: list, frenet_path_node_list: list):
+    """Nearest node + projection for each point (reference :364-426; every projection goes through the
+    match index of the first point, :413).  Returns (index list, [(x_r, y_r, theta_r, kappa_r), ...])."""
+    if len(xy_list) == 0:
+        return [], []
+    r = _runtime.planner().frenet_project(_line(frenet_path_node_list), points=_pts(xy_list), want=("match", "proj"))
+    return list(r["match"][0]), [tuple(v) for v in r["proj"][0]]
+
+
+def find_match_points(xy_list: list, frenet_path_node_list: list, is_first_run: bool, pre_match_index: int):
+    """Reference :49-182: first run scans from node 0 (early exit after 50); later runs scan from
+    pre_match_index forward or backward (early exit after 5)."""
+    if len(xy_list) == 0:
+        return [], []
+    pre = None if is_first_run is True else np.array([int(pre_match_index)], dtype=np.int32)
+    r = _runtime.planner().frenet_project(_line(frenet_path_node_list), points=_pts(xy_list), pre_match=pre,
+                                          want=("match", "proj"))
+    return list(r["match"][0]), [tuple(v) for v in r["proj"][0]]
+
+
+def sampling(match_point_index: int, frenet_path_node_list: list, back_length=10, forward_length=50):
+    """Local reference-line window (reference :231-259).  The arguments are ignored in favour of 10 back /
+    40 forward exactly like the reference (:244-245); pure list slicing, no arithmetic."""
+    back_length, forward_length = 10, 40
+    total = back_length + forward_length
+    if match_point_index < back_length:
+        back_length = match_point_index
+        forward_length = total - back_length
+    if (len(frenet_path_node_list) - match_point_index) - 1 < forward_length:
+        forward_length = len(frenet_path_node_list) - match_point_index - 1
+        back_length = total - forward_length
+    return list(frenet_path_node_list[match_point_index - back_length: match_point_index]) \
+        + list(frenet_path_node_list[match_point_index: match_point_index + forward_length + 1])
+
+
+def cal_s_map_fun(local_path_opt: list, origin_xy: tuple):
+    """s of every reference-line node relative to the ego projection (reference :448-472)."""
+    r = _runtime.planner().frenet_project(_line(local_path_opt), origin=np.array([[origin_xy[0], origin_xy[1]]]),
+                                          want=("s_map",))
+    return list(r["s_map"][0])
+
+
+def cal_s_l_fun(obs_xy_list: list, local_path_opt: list, s_map: list):
+    """Cartesian -> (s, l) for a list of points with the caller's s_map (reference :475-509)."""
+    if len(obs_xy_list) == 0:
+        return [], []
+    r = _runtime.planner().frenet_project(_line(local_path_opt), points=_pts(obs_xy_list),
+                                          s_map_in=np.asarray(s_map, dtype=np.float64)[None], want=("sl",))
+    return list(r["sl"][0, :, 0]), list(r["sl"][0, :, 1])
+
+
+def cal_s_l_deri_fun(xy_list: list, V_xy_list: list, a_xy_list: list, local_path_xy_opt: list, origin_xy: tuple):
+    """l, dl/dt, ds/dt, ddl/dt2, dl/ds, dds/dt2, ddl/ds2 lists (reference :512-588)."""
+    if len(xy_list) == 0:
+        return tuple([] for _ in range(7))
+    r = _runtime.planner().frenet_project(_line(local_path_xy_opt), origin=np.array([[origin_xy[0], origin_xy[1]]]),
+                                          points=_pts(xy_list), vel=_pts(V_xy_list), acc=_pts(a_xy_list),
+                                          want=("deriv",))
+    d = r["deriv"][0]
+    return tuple(list(d[:, k]) for k in range(7))

@@ -96,6 +96,8 @@ int emp_max_enriched(const EmpDpParams *p);   /* upper bound on n_enr for these 
 int emp_version(void);
 const char *emp_last_error(void);
 
+typedef struct EmpPlanner EmpPlanner;   /* host-buffer planner handle, see below */
+
 /* ---- device-pointer entry points -------------------------------------------*/
 
 /* S-L lattice DP + densify for a batch of frames, one launch.
@@ -131,12 +133,49 @@ int emp_corridor_dev(const double *dp_s, const double *dp_l, int n, const double
 int emp_sl_plan_dev(const double *scenes, int kmax, int batch, const EmpDpParams *dp,
                     const EmpQpParams *qp, int n_enr_max, double *plans, int32_t *rows, void *stream);
 
+/* ---- Cartesian <-> Frenet (K4) ---------------------------------------------------------
+ * lines: [batch, n_nodes, 4] reference line per scene as (x, y, theta, kappa) rows - the output of
+ * planning_utils.sampling (:231, 51 nodes) after smooth_reference_line (:262).  n_nodes*32 bytes must be
+ * a multiple of 16 (always true). */
+
+/* planning_utils.cal_s_map_fun (:448-472) for every scene, and - when `points` is not NULL -
+ * cal_s_l_fun (:475-509; match_projection_points :364, cal_projection_s_fun :429) for a list of up to
+ * max_points points per scene (npts[batch], NULL = all max_points) and, when vel/acc/deriv are not NULL,
+ * cal_s_l_deri_fun (:512-588) for the same points.
+ *   origin [batch,2]; points/vel/acc [batch,max_points,2];
+ *   s_map [batch,n_nodes]; match [batch,max_points] int32; sl [batch,max_points,2] = (s,l);
+ *   deriv [batch,max_points,7] = (l, dl/dt, ds/dt, ddl/dt2, dl/ds, dds/dt2, ddl/ds2);
+ *   proj [batch,max_points,4] = projection node (x_r, y_r, theta_r, kappa_r) of match_projection_points.
+ * s_map_in [batch,n_nodes] (optional): use this s-map instead of computing one from `origin` (cal_s_l_fun is
+ * called with the caller's s_map).  pre_match [batch] (optional): planning_utils.find_match_points (:49-182)
+ * with is_first_run=False - scan from that node, forward or backward, early exit after 5.  Outputs may be NULL. */
+int emp_frenet_project_dev(const double *lines, int n_nodes, const double *origin, const double *points,
+                           const int32_t *npts, int max_points, const double *vel, const double *acc,
+                           const double *s_map_in, const int32_t *pre_match, int batch,
+                           double *s_map, int32_t *match, double *proj, double *sl, double *deriv, void *stream);
+
+/* path_planning.frenet_2_x_y_theta_kappa (:15-46, everything before the trailing smooth_reference_line) with
+ * cal_proj_point (:52-75).  start_sl [batch,2]; path_s/path_l [batch,max_points]; npath[batch] (NULL = all);
+ * cart [batch, max_points+1, 4]: row 0 = (x, y, NaN, NaN) of the plan start, then (x, y, theta, kappa);
+ * ncart[batch] = rows written (truncated where s > s_map[-1], :40-41), -1 if the start is beyond the map. */
+int emp_frenet_to_cart_dev(const double *lines, const double *s_map, int n_nodes, const double *start_sl,
+                           const double *path_s, const double *path_l, const int32_t *npath, int max_points,
+                           int batch, double *cart, int32_t *ncart, void *stream);
+
+/* Host-buffer versions (temporary device buffers on the planner's stream). */
+int emp_frenet_project_host(EmpPlanner *pl, const double *lines, int n_nodes, const double *origin,
+                            const double *points, const int32_t *npts, int max_points, const double *vel,
+                            const double *acc, const double *s_map_in, const int32_t *pre_match, int batch,
+                            double *s_map, int32_t *match, double *proj, double *sl, double *deriv);
+int emp_frenet_to_cart_host(EmpPlanner *pl, const double *lines, const double *s_map, int n_nodes,
+                            const double *start_sl, const double *path_s, const double *path_l,
+                            const int32_t *npath, int max_points, int batch, double *cart, int32_t *ncart);
+
 /* FP64 FMA micro-benchmark (roofline denominator; absent from MEASURED_PEAKS.json).
  * Returns achieved TFLOP/s through *tflops. */
 int emp_fp64_peak(int iters, double *tflops, double *ms);
 
 /* ---- host-buffer entry points ----------------------------------------------*/
-typedef struct EmpPlanner EmpPlanner;
 
 /* device < 0: current device.  CUDA is initialised here, not at library load
  * (the reference calls the planner from a forked child, test_9.py:226-227). */

@@ -1,0 +1,108 @@
+"""GPU parity tests for the Cartesian<->Frenet kernels (csrc/frenet.cu) through the C ABI, against golden
+outputs of the unmodified reference (tests/golden/frenet.npz) and the oracle.  Tolerance: 1e-9 absolute
+(SURVEY.md §8(c)); indices exact."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, load_golden
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-9
+
+
+@pytest.fixture(scope="module")
+def planner():
+    from emplanner_carla_b200 import api
+    pl = api.HostPlanner(max_batch=64)
+    yield pl
+    pl.close()
+
+
+def test_batched_projection_against_reference_golden(planner):
+    g = load_golden("frenet.npz")
+    F = len(g["ego"])
+    r = planner.frenet_project(g["line"], origin=g["ego"], points=g["obs_xy"], want=("s_map", "match", "sl"))
+    assert np.abs(r["s_map"] - g["smap"]).max() < TOL
+    assert np.abs(r["sl"][:, :, 0] - g["obs_s"]).max() < TOL and np.abs(r["sl"][:, :, 1] - g["obs_l"]).max() < TOL
+    # plan-start derivatives: cal_s_l_deri_fun([ego], [v], [a], line, ego)
+    d = planner.frenet_project(g["line"], origin=g["ego"], points=g["ego"][:, None, :], vel=g["vel"][:, None, :],
+                               acc=g["acc"][:, None, :], want=("deriv",))
+    assert np.abs(d["deriv"][:, 0, :] - g["deriv"]).max() < TOL
+    # find_match_points(is_first_run=False) on the long global path, one scene per golden frame
+    gp = np.broadcast_to(g["global_path"], (F,) + g["global_path"].shape)
+    m = planner.frenet_project(gp, points=g["ego"][:, None, :], pre_match=g["pre_idx"], want=("match",))
+    assert np.array_equal(m["match"][:, 0], g["match_idx"])
+    assert F >= 8
+
+
+def test_frenet_to_cartesian_against_reference_golden(planner):
+    g = load_golden("frenet.npz")
+    cart, ncart = planner.frenet_to_cart(g["line"], g["smap"], g["start_sl"], g["path_s"], g["path_l"])
+    for f in range(len(ncart)):
+        ref = g["cart_raw"][f]
+        n_ref = int(np.sum(~np.isnan(ref[:, 0])))
+        assert ncart[f] == n_ref                                   # truncation at s_map[-1] (Q14)
+        assert np.abs(cart[f, 0, :2] - ref[0, :2]).max() < TOL
+        assert np.abs(cart[f, 1:n_ref] - ref[1:n_ref]).max() < TOL
+    assert (ncart < g["path_s"].shape[1] + 1).any(), "golden set must exercise the truncation"
+
+
+def test_quirk_q12_first_point_index_and_ragged_lists(planner):
+    """Obstacle #i>0 is projected through obstacle #0's match node (planning_utils.py:413); ragged point
+    counts; empty lists."""
+    from oracle import frenet as ofr
+    g = load_golden("frenet.npz")
+    line = [tuple(r) for r in g["line"][0]]
+    smap = list(g["smap"][0])
+    pts = [tuple(p) for p in g["obs_xy"][0]]
+    s_o, l_o = ofr.s_l(pts, line, smap)
+    s_rev, l_rev = ofr.s_l(pts[::-1], line, smap)
+    assert abs(l_o[1] - l_rev[2]) > 1e-6, "scene must make the quirk observable"
+    npts = np.array([4, 2, 0], dtype=np.int32)
+    r = planner.frenet_project(g["line"][:3], points=g["obs_xy"][:3], npts=npts, s_map_in=g["smap"][:3], want=("sl",))
+    assert np.abs(r["sl"][0, :, 0] - s_o).max() < TOL and np.abs(r["sl"][0, :, 1] - l_o).max() < TOL
+    s1, l1 = ofr.s_l([tuple(p) for p in g["obs_xy"][1, :2]], [tuple(v) for v in g["line"][1]], list(g["smap"][1]))
+    assert np.abs(r["sl"][1, :2, 0] - s1).max() < TOL and np.abs(r["sl"][1, :2, 1] - l1).max() < TOL
+    assert np.all(r["sl"][1, 2:] == 0) and np.all(r["sl"][2] == 0)
+
+
+def test_dropin_planning_utils_sequence(planner):
+    """The reference's call sequence test_9.py:99-134,172,213 with the reference's function names."""
+    pkg_dir = os.path.join(ROOT, "emplanner_carla_b200")
+    sys.path.insert(0, pkg_dir)
+    for k in [k for k in sys.modules if k == "planner" or k.startswith("planner.")]:
+        del sys.modules[k]
+    try:
+        from planner import path_planning, planning_utils
+        g = load_golden("frenet.npz")
+        gp = [tuple(r) for r in g["global_path"]]
+        for f in range(3):
+            ego = tuple(g["ego"][f])
+            mi, _ = planning_utils.find_match_points(xy_list=[ego], frenet_path_node_list=gp, is_first_run=False,
+                                                     pre_match_index=int(g["pre_idx"][f]))
+            assert mi[0] == g["match_idx"][f]
+            local = planning_utils.sampling(mi[0], gp, back_length=10, forward_length=50)
+            assert np.array_equal(np.array(local), g["local"][f])
+            line = [tuple(r) for r in g["line"][f]]          # smooth_reference_line output of the reference
+            s_map = planning_utils.cal_s_map_fun(line, origin_xy=ego)
+            assert isinstance(s_map, list) and np.abs(np.array(s_map) - g["smap"][f]).max() < TOL
+            obs_s, obs_l = planning_utils.cal_s_l_fun([tuple(p) for p in g["obs_xy"][f]], line, s_map)
+            assert np.abs(np.array(obs_s) - g["obs_s"][f]).max() < TOL
+            assert np.abs(np.array(obs_l) - g["obs_l"][f]).max() < TOL
+            der = planning_utils.cal_s_l_deri_fun(xy_list=[ego], V_xy_list=[tuple(g["vel"][f])],
+                                                  a_xy_list=[tuple(g["acc"][f])], local_path_xy_opt=line, origin_xy=ego)
+            assert len(der) == 7 and np.abs(np.array([d[0] for d in der]) - g["deriv"][f]).max() < TOL
+            idx, proj = planning_utils.match_projection_points([ego], line)
+            raw = path_planning.frenet_2_x_y_theta_kappa(g["start_sl"][f, 0], g["start_sl"][f, 1], list(g["path_s"][f]),
+                                                         list(g["path_l"][f]), line, s_map, smooth=False)
+            n_ref = int(np.sum(~np.isnan(g["cart_raw"][f][:, 0])))
+            assert len(raw) == n_ref and np.abs(np.array(raw[1:]) - g["cart_raw"][f, 1:n_ref]).max() < TOL
+            x, y, th, kap, m = path_planning.cal_proj_point(g["path_s"][f, 3], 0, line, s_map)
+            assert abs(th - g["cart_raw"][f, 4, 2]) < TOL and kap == g["cart_raw"][f, 4, 3]
+    finally:
+        sys.path.remove(pkg_dir)
+        for k in [k for k in sys.modules if k == "planner" or k.startswith("planner.")]:
+            del sys.modules[k]
