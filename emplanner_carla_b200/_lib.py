@@ -27,6 +27,12 @@ class QpParams(C.Structure):
                 ("feastol", C.c_double), ("maxiters", C.c_int32), ("reserved", C.c_int32)]
 
 
+class StParams(C.Structure):
+    """EmpStParams: speed_DP keyword defaults (reference speed_planning_test.py:101-102)."""
+    _fields_ = [("reference_speed", C.c_double), ("w_ref_speed", C.c_double), ("w_accel", C.c_double),
+                ("w_obs", C.c_double)]
+
+
 _P = C.c_void_p
 _DPP = C.POINTER(DpParams)
 _QPP = C.POINTER(QpParams)
@@ -47,6 +53,9 @@ _SIGNATURES = {
     "emp_frenet_to_cart_dev": (C.c_int, [_P, _P, C.c_int, _P, _P, _P, _P, C.c_int, C.c_int, _P, _P, _P]),
     "emp_frenet_project_host": (C.c_int, [_P, _P, C.c_int, _P, _P, _P, C.c_int, _P, _P, _P, _P, C.c_int, _P, _P, _P, _P, _P]),
     "emp_frenet_to_cart_host": (C.c_int, [_P, _P, _P, C.c_int, _P, _P, _P, _P, C.c_int, C.c_int, _P, _P]),
+    "emp_st_params_default": (None, [C.POINTER(StParams)]),
+    "emp_st_dp_dev": (C.c_int, [_P, C.c_int, C.c_int, C.POINTER(StParams), _P, _P, _P, _P, _P]),
+    "emp_st_dp_host": (C.c_int, [_P, _P, C.c_int, C.c_int, C.POINTER(StParams), _P, _P, _P, _P]),
     "emp_fp64_peak": (C.c_int, [C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "emp_planner_create": (C.c_int, [C.POINTER(_P), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),
     "emp_planner_destroy": (None, [_P]),
@@ -112,4 +121,11 @@ def qp_params(dp_sampling_res=2, w_cost_l=1000, w_cost_dl=10000, w_cost_ddl=3000
     p.obs_length, p.obs_width = float(obs_length), float(obs_width)
     p.abstol, p.reltol, p.feastol = float(abstol), float(reltol), float(feastol)
     p.maxiters = int(maxiters)
+    return p
+
+
+def st_params(reference_speed=50, w_cost_ref_speed=4000, w_cost_accel=100, w_cost_obs=10000000):
+    p = StParams()
+    p.reference_speed, p.w_ref_speed = float(reference_speed), float(w_cost_ref_speed)
+    p.w_accel, p.w_obs = float(w_cost_accel), float(w_cost_obs)
     return p

@@ -13,7 +13,7 @@ import ctypes as C
 import numpy as np
 
 from . import _lib
-from ._lib import EmpError, dp_params, qp_params  # noqa: F401  (re-exported)
+from ._lib import EmpError, dp_params, qp_params, st_params  # noqa: F401  (re-exported)
 
 PLAN_HDR = 8
 SCENE_HDR = 6
@@ -54,6 +54,36 @@ def pack_scenes(obs_s, obs_l, nobs, s0, l0, dl0, ddl0, kmax=8):
     rec[:, SCENE_HDR:SCENE_HDR + k_in] = np.nan_to_num(obs_s, nan=0.0)
     rec[:, SCENE_HDR + kmax:SCENE_HDR + kmax + k_in] = np.nan_to_num(obs_l, nan=0.0)
     return rec
+
+
+ST_OUT_STRIDE = 40
+
+
+def pack_st_scenes(s_in, s_out, t_in, t_out, v0, kmax=8):
+    """[B, 2+4*kmax] S-T scene records: [plan_start_s_dot, -, s_in, s_out, t_in, t_out]; NaN s_in = absent."""
+    v0 = np.atleast_1d(np.asarray(v0, dtype=np.float64))
+    B = v0.shape[0]
+    rec = np.full((B, 2 + 4 * kmax), np.nan)
+    rec[:, 0] = v0
+    rec[:, 1] = 0.0
+    for q, a in enumerate((s_in, s_out, t_in, t_out)):
+        a = np.asarray(a, dtype=np.float64).reshape(B, -1)
+        if a.shape[1] > kmax:
+            raise ValueError("more obstacle slots than kmax")
+        rec[:, 2 + q * kmax:2 + q * kmax + a.shape[1]] = a
+    return rec
+
+
+def st_dp_device(scenes, st, out=None):
+    """speed_DP on a [B, 2+4*kmax] float64 CUDA tensor; enqueues one kernel on torch's current stream."""
+    import torch
+    B = scenes.shape[0]
+    kmax = (scenes.shape[1] - 2) // 4
+    if out is None:
+        out = torch.empty((B, ST_OUT_STRIDE), dtype=torch.float64, device=scenes.device)
+    _lib.check(_lib.lib().emp_st_dp_dev(_dev_ptr(scenes), kmax, B, C.byref(st), _dev_ptr(out), None, None, None,
+                                        _stream_ptr()))
+    return out
 
 
 class PlanView:
@@ -211,6 +241,26 @@ class HostPlanner:
                                                       _ptr(path_l), _ptr(npath) if npath is not None else None, M, B,
                                                       _ptr(cart), _ptr(ncart)))
         return cart, ncart
+
+    # ---- S-T speed DP (K3) --------------------------------------------------------------------
+    def st_dp(self, scenes, st, want_tables=False):
+        """speed_DP for a batch.  scenes [B, 2+4*kmax] (pack_st_scenes).  Returns dict(min_row, min_col, min_cost,
+        dp_s [B,16], dp_t [B,16] and, if want_tables, cost/s_dot [B,40,16] float64, node [B,40,16] int32)."""
+        scenes = np.ascontiguousarray(scenes, dtype=np.float64)
+        B = scenes.shape[0]
+        kmax = (scenes.shape[1] - 2) // 4
+        out = np.zeros((B, ST_OUT_STRIDE))
+        cost = np.zeros((B, 40, 16)) if want_tables else None
+        sdot = np.zeros((B, 40, 16)) if want_tables else None
+        node = np.zeros((B, 40, 16), dtype=np.int32) if want_tables else None
+        o = lambda a: _ptr(a) if a is not None else None
+        _lib.check(_lib.lib().emp_st_dp_host(self._h, _ptr(scenes), kmax, B, C.byref(st), _ptr(out), o(cost), o(sdot),
+                                             o(node)))
+        r = dict(min_row=out[:, 0].astype(np.int32), min_col=out[:, 1].astype(np.int32), min_cost=out[:, 2].copy(),
+                 dp_s=out[:, 8:24].copy(), dp_t=out[:, 24:40].copy())
+        if want_tables:
+            r.update(cost=cost, s_dot=sdot, node=node)
+        return r
 
     @property
     def last_kernel_ms(self):

@@ -8,6 +8,7 @@
 #include "emp_common.cuh"
 #include "sl_kernels.h"
 #include "frenet_kernels.h"
+#include "st_kernels.h"
 
 namespace {
 
@@ -122,6 +123,10 @@ struct EmpPlanner {
 
 extern "C" {
 
+void emp_st_params_default(EmpStParams *p) {
+    p->reference_speed = 50; p->w_ref_speed = 4000; p->w_accel = 100; p->w_obs = 10000000;
+}
+
 void emp_dp_params_default(EmpDpParams *p) {
     p->sampling_res = 2; p->w_collision = 1e12;
     p->w_smooth[0] = 300; p->w_smooth[1] = 1000; p->w_smooth[2] = 5000;
@@ -231,6 +236,18 @@ int emp_frenet_to_cart_dev(const double *lines, const double *s_map, int n_nodes
     cudaError_t e = emp::launch_frenet_to_cart(lines, s_map, start_sl, path_s, path_l, npath, cart, ncart, L,
                                                (cudaStream_t)stream);
     return e == cudaSuccess ? 0 : fail_cuda(e, "frenet_to_cart launch");
+}
+
+int emp_st_dp_dev(const double *scenes, int kmax, int batch, const EmpStParams *p, double *out, double *cost_tab,
+                  double *sdot_tab, int32_t *node_tab, void *stream) {
+    if (!p) return fail(-1, "EmpStParams is NULL");
+    if (kmax < 0 || kmax > EMP_ST_KMAX || (kmax & 1)) return fail(-2, "kmax must be even and in [0, 16]");
+    if (batch < 0) return fail(-2, "bad batch");
+    if (batch == 0) return 0;
+    if (!scenes || !out) return fail(-1, "scenes/out is NULL");
+    emp::StLaunch L{*p, batch, kmax, 2 + 4 * kmax};
+    cudaError_t e = emp::launch_st_dp(scenes, out, cost_tab, sdot_tab, node_tab, L, (cudaStream_t)stream);
+    return e == cudaSuccess ? 0 : fail_cuda(e, "st_dp launch");
 }
 
 int emp_fp64_peak(int iters, double *tflops, double *ms) {
@@ -449,6 +466,38 @@ int emp_frenet_to_cart_host(EmpPlanner *pl, const double *lines, const double *s
         }
     }
     EMP_CK(cudaStreamSynchronize(pl->stream), "planner stream");
+    return rc;
+}
+
+int emp_st_dp_host(EmpPlanner *pl, const double *scenes, int kmax, int batch, const EmpStParams *p, double *out,
+                   double *cost_tab, double *sdot_tab, int32_t *node_tab) {
+    if (!pl || !scenes || !out) return fail(-1, "NULL argument");
+    if (batch <= 0) return batch == 0 ? 0 : fail(-2, "bad batch");
+    if (kmax < 0 || kmax > EMP_ST_KMAX || (kmax & 1)) return fail(-2, "kmax must be even and in [0, 16]");
+    EMP_CK(cudaSetDevice(pl->device), "cudaSetDevice");
+    const size_t B = batch, T = (size_t)EMP_ST_ROWS * EMP_ST_COLS;
+    int rc;
+    {
+        Tmp t(pl->stream);
+        const double *d_sc = t.in(scenes, B * (2 + 4 * kmax));
+        double *d_out = t.out<double>(B * EMP_ST_OUT_STRIDE);
+        double *d_cost = cost_tab ? t.out<double>(B * T) : nullptr;
+        double *d_sdot = sdot_tab ? t.out<double>(B * T) : nullptr;
+        int32_t *d_node = node_tab ? t.out<int32_t>(B * T) : nullptr;
+        if (t.err != cudaSuccess) return fail_cuda(t.err, "st_dp_host staging");
+        EMP_CK(cudaEventRecord(pl->ev0, pl->stream), "event");
+        rc = emp_st_dp_dev(d_sc, kmax, batch, p, d_out, d_cost, d_sdot, d_node, pl->stream);
+        EMP_CK(cudaEventRecord(pl->ev1, pl->stream), "event");
+        if (rc == 0) {
+            t.back(out, d_out, B * EMP_ST_OUT_STRIDE);
+            t.back(cost_tab, d_cost, B * T);
+            t.back(sdot_tab, d_sdot, B * T);
+            t.back(node_tab, d_node, B * T);
+            if (t.err != cudaSuccess) return fail_cuda(t.err, "st_dp_host copy-back");
+        }
+    }
+    EMP_CK(cudaStreamSynchronize(pl->stream), "planner stream");
+    cudaEventElapsedTime(&pl->last_ms, pl->ev0, pl->ev1);
     return rc;
 }
 

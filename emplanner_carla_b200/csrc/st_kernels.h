@@ -1,0 +1,18 @@
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "../../include/emplanner.h"
+
+namespace emp {
+
+constexpr int ST_THREADS = 128;
+
+struct StLaunch {
+    EmpStParams prm;
+    int batch, kmax, scene_stride;
+};
+
+cudaError_t launch_st_dp(const double *scenes, double *out, double *cost_tab, double *sdot_tab, int32_t *node_tab,
+                         const StLaunch &p, cudaStream_t st);
+
+}  // namespace emp

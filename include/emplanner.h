@@ -33,6 +33,10 @@ extern "C" {
 #define EMP_MAX_ROW 16           /* lattice rows supported by the DP kernel */
 #define EMP_MAX_KMAX 32          /* obstacle slots per scene record */
 #define EMP_MAX_QP_POINTS 32     /* QP stations per frame (one warp lane each) */
+#define EMP_ST_KMAX 16           /* dynamic-obstacle slots per S-T scene record */
+#define EMP_ST_ROWS 40           /* s samples of the S-T lattice, speed_planning_test.py:114 */
+#define EMP_ST_COLS 16           /* t samples (0.5 s), speed_planning_test.py:116 */
+#define EMP_ST_OUT_STRIDE 40     /* words per S-T result record */
 
 /* ---- per-frame status bits ------------------------------------------------ */
 #define EMP_DP_NO_OBSTACLE      0x1   /* K == 0: straight branch, path_planning.py:362-363 */
@@ -68,6 +72,14 @@ typedef struct EmpQpParams {          /* Quadratic_planning :78-81, cal_lmin_lma
     int32_t reserved;
 } EmpQpParams;
 
+typedef struct EmpStParams {          /* speed_DP, speed_planning_test.py:101-102 */
+    double reference_speed;           /* 50 */
+    double w_ref_speed;               /* 4000 */
+    double w_accel;                   /* 100 */
+    double w_obs;                     /* 10000000 */
+} EmpStParams;
+
+void emp_st_params_default(EmpStParams *p);
 void emp_dp_params_default(EmpDpParams *p);
 void emp_qp_params_default(EmpQpParams *p);
 
@@ -170,6 +182,20 @@ int emp_frenet_project_host(EmpPlanner *pl, const double *lines, int n_nodes, co
 int emp_frenet_to_cart_host(EmpPlanner *pl, const double *lines, const double *s_map, int n_nodes,
                             const double *start_sl, const double *path_s, const double *path_l,
                             const int32_t *npath, int max_points, int batch, double *cart, int32_t *ncart);
+
+/* ---- S-T speed DP (K3) -----------------------------------------------------------------
+ * Replaces speed_planning_test.speed_DP (:101-188) with CalcDpCost (:191), CalcObsCost (:234),
+ * CalcCollisionCost (:274), CalcSTCoordinate (:287), for a batch of frames, one launch.
+ * scenes: [batch, 2 + 4*kmax] words = [plan_start_s_dot, -, s_in[kmax], s_out[kmax], t_in[kmax], t_out[kmax]],
+ *   NaN s_in = absent obstacle (like the reference, :255); kmax <= EMP_ST_KMAX, even.
+ * out: [batch, EMP_ST_OUT_STRIDE] words = [min_row, min_col, min_cost, -,-,-,-,-, dp_speed_s[16], dp_speed_t[16]]
+ *   (NaN beyond min_col, like the reference's output initialisation :155).
+ * cost_tab / sdot_tab [batch,40,16] float64 and node_tab [batch,40,16] int32: optional copies of the
+ *   reference's dp_st_cost / dp_st_s_dot / dp_st_node tables (NULL to skip). */
+int emp_st_dp_dev(const double *scenes, int kmax, int batch, const EmpStParams *p, double *out,
+                  double *cost_tab, double *sdot_tab, int32_t *node_tab, void *stream);
+int emp_st_dp_host(EmpPlanner *pl, const double *scenes, int kmax, int batch, const EmpStParams *p, double *out,
+                   double *cost_tab, double *sdot_tab, int32_t *node_tab);
 
 /* FP64 FMA micro-benchmark (roofline denominator; absent from MEASURED_PEAKS.json).
  * Returns achieved TFLOP/s through *tflops. */
