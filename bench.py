@@ -221,8 +221,9 @@ def main():
     shard = {k: v[rank * B:(rank + 1) * B] for k, v in sc.items()}
     rec_host = api.pack_scenes(**shard)
     scenes_d = torch.from_numpy(rec_host).to(dev)
-    gathered = torch.zeros((world, B, stride), dtype=torch.float64, device=dev)
-    mine = gathered[rank]                                              # kernels write straight into the send slice
+    from emplanner_carla_b200 import sharding
+    gbuf = sharding.GatherBuffer(B, stride, dev)
+    mine = gbuf.mine                                                   # kernels write straight into the send slice
     flush = None if args.no_flush else torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     stream = torch.cuda.current_stream()
 
@@ -236,7 +237,7 @@ def main():
         if ev:
             ev[2].record(stream)
         if world > 1:
-            dist.all_gather_into_tensor(gathered.view(-1), mine.view(-1))
+            gbuf.all_gather()                                          # one in-place NCCL all-gather of plan records
         if ev:
             ev[3].record(stream)
 
@@ -347,7 +348,7 @@ def main():
                     "peak_source": "emp_fp64_peak FMA micro-benchmark, this GPU, this run"},
         "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": int(rec_host.nbytes),
                 "d2h_bytes_per_step": int(out.nbytes), "api": "emp_sl_plan_host via HostPlanner.plan"},
-        "gpu_launches": 2 * args.steps,
+        "gpu_launches": 2 * args.steps, "collectives": (args.steps if world > 1 else 0),
         "clocks": clocks,
     }
     if cpu:
