@@ -77,13 +77,18 @@ __device__ __forceinline__ int warp_argmin(double v, int lane) {
 
 struct Factor {                 // per-lane pieces of the KKT factorisation
     double q00, q01, q11, q22;  // Q upper triangular, S_i^-1 = Q Q'
-    double l10, l20, l21;       // strict lower part of the Cholesky block L_ii of stage i (pair i,i+1)
-    double i00, i11, i22;       // 1 / diag(L_ii)
-    double m[9];                // M_i = L_{i-1}^-1 (F X_i E'), row-major
+    double l10, l20, l21;       // strict lower part of the Cholesky factor L of this stage's pivot block
+    double i00, i11, i22;       // 1 / diag(L)
+    double xl[9], xr[9];        // XL = L^-1 K(i, i-d), XR = L^-1 K(i, i+d) at the level the stage was eliminated
 };
 
+// Block cyclic reduction (nested-dissection Cholesky) of the block-tridiagonal K: at level d = 1,2,4,8,16 the
+// stages with (lane mod 2d) == d-1 are eliminated against their current neighbours lane-d and lane+d, which
+// stay with (lane mod 2d) == 2d-1.  Five levels instead of n-1 sequential steps, every level lane-parallel.
+#define EMP_CR_LEVELS 5
+
 #ifndef EMP_QP_MINBLOCKS
-#define EMP_QP_MINBLOCKS 4
+#define EMP_QP_MINBLOCKS 2
 #endif
 
 __global__ void __launch_bounds__(QP_WARPS * 32, EMP_QP_MINBLOCKS)
@@ -280,45 +285,75 @@ sl_qp_kernel(const double *__restrict__ scenes, double *__restrict__ plans, doub
             const double k20 = e20 + shfl_down(f20, 1);
             const double k21 = e21 + shfl_down(f21, 1);
             const double k22 = (e22 + shfl_down(f22, 1)) + jinv;
-            F.l10 = 0.0; F.l20 = 0.0; F.l21 = 0.0;
-            F.i00 = 1.0; F.i11 = 1.0; F.i22 = 1.0;
+            // pivot block D, couplings CL = K(i, i-1) = B', CR = K(i, i+1) = B of the next lane
+            double D00 = k00, D10 = k10, D11 = k11, D20 = k20, D21 = k21, D22 = k22;
+            double CL[9], CR[9];
             EMP_UNROLL
-            for (int k = 0; k < 9; ++k) F.m[k] = 0.0;
+            for (int r = 0; r < 3; ++r) {
+                EMP_UNROLL
+                for (int c = 0; c < 3; ++c) {
+                    CL[3 * r + c] = (stage && lane > 0) ? B[3 * c + r] : 0.0;
+                    const double nb = shfl_down(B[3 * r + c], 1);
+                    CR[3 * r + c] = (lane < n - 2) ? nb : 0.0;
+                }
+            }
+            if (!stage) { D00 = 1.0; D10 = 0.0; D11 = 1.0; D20 = 0.0; D21 = 0.0; D22 = 1.0; }
             bool bad = false;
-            for (int i = 0; i < n - 1; ++i) {
-                const int src = i > 0 ? i - 1 : 0;
-                const double pl10 = shfl(F.l10, src), pl20 = shfl(F.l20, src), pl21 = shfl(F.l21, src);
-                const double pi00 = shfl(F.i00, src), pi11 = shfl(F.i11, src), pi22 = shfl(F.i22, src);
-                if (lane == i) {                                  // only the owner of stage i works
-                    if (i > 0) {
-                        EMP_UNROLL
-                        for (int c = 0; c < 3; ++c) {             // M = L_{i-1}^-1 B, column c
-                            const double m0 = B[c] * pi00;
-                            const double m1 = (B[3 + c] - pl10 * m0) * pi11;
-                            const double m2 = ((B[6 + c] - pl20 * m0) - pl21 * m1) * pi22;
-                            F.m[c] = m0;
-                            F.m[3 + c] = m1;
-                            F.m[6 + c] = m2;
-                        }
-                    }
-                    const double *M = F.m;
-                    // D = K_ii - M'M
-                    const double d00 = k00 - (M[0] * M[0] + M[3] * M[3] + M[6] * M[6]);
-                    const double d10 = k10 - (M[1] * M[0] + M[4] * M[3] + M[7] * M[6]);
-                    const double d11 = k11 - (M[1] * M[1] + M[4] * M[4] + M[7] * M[7]);
-                    const double d20 = k20 - (M[2] * M[0] + M[5] * M[3] + M[8] * M[6]);
-                    const double d21 = k21 - (M[2] * M[1] + M[5] * M[4] + M[8] * M[7]);
-                    const double d22 = k22 - (M[2] * M[2] + M[5] * M[5] + M[8] * M[8]);
-                    const double j00 = rsqrt(d00);
-                    const double c10 = d10 * j00, c20 = d20 * j00;
-                    const double t11 = d11 - c10 * c10;
+            EMP_UNROLL
+            for (int lev = 0; lev < EMP_CR_LEVELS; ++lev) {
+                const int d = 1 << lev, msk = 2 * d - 1;
+                const bool el = (lane & msk) == d - 1;
+                const bool rm = (lane & msk) == msk;
+                if (el) {
+                    const double j00 = rsqrt(D00);
+                    const double c10 = D10 * j00, c20 = D20 * j00;
+                    const double t11 = D11 - c10 * c10;
                     const double j11 = rsqrt(t11);
-                    const double c21 = (d21 - c20 * c10) * j11;
-                    const double t22 = (d22 - c20 * c20) - c21 * c21;
+                    const double c21 = (D21 - c20 * c10) * j11;
+                    const double t22 = (D22 - c20 * c20) - c21 * c21;
                     const double j22 = rsqrt(t22);
-                    bad = !(d00 > 0.0) || !(t11 > 0.0) || !(t22 > 0.0) || !isfinite(j00 + j11 + j22);
+                    bad = bad || (stage && (!(D00 > 0.0) || !(t11 > 0.0) || !(t22 > 0.0) || !isfinite(j00 + j11 + j22)));
                     F.l10 = c10; F.l20 = c20; F.l21 = c21;
                     F.i00 = j00; F.i11 = j11; F.i22 = j22;
+                    EMP_UNROLL
+                    for (int c = 0; c < 3; ++c) {                 // X = L^-1 C, column c
+                        const double a0 = CL[c] * j00;
+                        const double a1 = (CL[3 + c] - c10 * a0) * j11;
+                        F.xl[c] = a0; F.xl[3 + c] = a1; F.xl[6 + c] = ((CL[6 + c] - c20 * a0) - c21 * a1) * j22;
+                        const double b0 = CR[c] * j00;
+                        const double b1 = (CR[3 + c] - c10 * b0) * j11;
+                        F.xr[c] = b0; F.xr[3 + c] = b1; F.xr[6 + c] = ((CR[6 + c] - c20 * b0) - c21 * b1) * j22;
+                    }
+                }
+                // products of the eliminated stages, handed to the remaining neighbours element by element
+                const bool has_a = lane - d >= 0, has_b = lane + d < 32;
+                EMP_UNROLL
+                for (int r = 0; r < 3; ++r) {
+                    EMP_UNROLL
+                    for (int c = 0; c < 3; ++c) {
+                        const double plr = el ? (F.xl[r] * F.xr[c] + F.xl[3 + r] * F.xr[3 + c]) + F.xl[6 + r] * F.xr[6 + c] : 0.0;
+                        const double fa = shfl_up(plr, d);        // (XL'XR)[r][c] of lane-d
+                        const double fb = shfl_down(plr, d);      // (XL'XR)[r][c] of lane+d
+                        if (rm) {
+                            CL[3 * c + r] = has_a ? -fa : 0.0;    // K(j, j-2d) = -(XL'XR of a)'
+                            CR[3 * r + c] = has_b ? -fb : 0.0;    // K(j, j+2d) = -(XL'XR of b)
+                        }
+                        if (c <= r) {
+                            const double prr = el ? (F.xr[r] * F.xr[c] + F.xr[3 + r] * F.xr[3 + c]) + F.xr[6 + r] * F.xr[6 + c] : 0.0;
+                            const double pll = el ? (F.xl[r] * F.xl[c] + F.xl[3 + r] * F.xl[3 + c]) + F.xl[6 + r] * F.xl[6 + c] : 0.0;
+                            const double ga = shfl_up(prr, d);    // (XR'XR) of lane-d
+                            const double gb = shfl_down(pll, d);  // (XL'XL) of lane+d
+                            const double upd = (has_a ? ga : 0.0) + (has_b ? gb : 0.0);
+                            if (rm) {
+                                if (r == 0) D00 -= upd;
+                                else if (r == 1 && c == 0) D10 -= upd;
+                                else if (r == 1) D11 -= upd;
+                                else if (c == 0) D20 -= upd;
+                                else if (c == 1) D21 -= upd;
+                                else D22 -= upd;
+                            }
+                        }
+                    }
                 }
             }
             broke = __any_sync(EMP_FULL_MASK, bad);
@@ -344,33 +379,50 @@ sl_qp_kernel(const double *__restrict__ scenes, double *__restrict__ plans, doub
             double r0 = ((xg[0] + G.a * xg[1]) + G.b * xg[2]) + shfl_down(fx0, 1) - by[0];
             double r1 = (xg[1] + G.e * xg[2]) + shfl_down(fx1, 1) - by[1];
             double r2 = nojerk ? 0.0 : xg[2] + shfl_down(fx2, 1);
-            // forward substitution chain  t_i = L_ii^-1 (r_i - M_i' t_{i-1})
+            // forward elimination, level by level: t_i = L_i^-1 r_i, then r_{i-d} -= XL' t_i, r_{i+d} -= XR' t_i
+            if (!stage) { r0 = 0.0; r1 = 0.0; r2 = 0.0; }
             double t0 = 0.0, t1 = 0.0, t2 = 0.0;
-            for (int i = 0; i < n - 1; ++i) {
-                const int src = i > 0 ? i - 1 : 0;
-                const double p0 = shfl(t0, src), p1 = shfl(t1, src), p2 = shfl(t2, src);
-                if (lane == i) {
-                    const double rr0 = r0 - ((F.m[0] * p0 + F.m[3] * p1) + F.m[6] * p2);
-                    const double rr1 = r1 - ((F.m[1] * p0 + F.m[4] * p1) + F.m[7] * p2);
-                    const double rr2 = r2 - ((F.m[2] * p0 + F.m[5] * p1) + F.m[8] * p2);
-                    t0 = rr0 * F.i00;
-                    t1 = (rr1 - F.l10 * t0) * F.i11;
-                    t2 = ((rr2 - F.l20 * t0) - F.l21 * t1) * F.i22;
+            EMP_UNROLL
+            for (int lev = 0; lev < EMP_CR_LEVELS; ++lev) {
+                const int d = 1 << lev, msk = 2 * d - 1;
+                const bool el = (lane & msk) == d - 1;
+                const bool rm = (lane & msk) == msk;
+                double ul0 = 0.0, ul1 = 0.0, ul2 = 0.0, ur0 = 0.0, ur1 = 0.0, ur2 = 0.0;
+                if (el) {
+                    t0 = r0 * F.i00;
+                    t1 = (r1 - F.l10 * t0) * F.i11;
+                    t2 = ((r2 - F.l20 * t0) - F.l21 * t1) * F.i22;
+                    ul0 = (F.xl[0] * t0 + F.xl[3] * t1) + F.xl[6] * t2;
+                    ul1 = (F.xl[1] * t0 + F.xl[4] * t1) + F.xl[7] * t2;
+                    ul2 = (F.xl[2] * t0 + F.xl[5] * t1) + F.xl[8] * t2;
+                    ur0 = (F.xr[0] * t0 + F.xr[3] * t1) + F.xr[6] * t2;
+                    ur1 = (F.xr[1] * t0 + F.xr[4] * t1) + F.xr[7] * t2;
+                    ur2 = (F.xr[2] * t0 + F.xr[5] * t1) + F.xr[8] * t2;
+                }
+                const double a0 = shfl_up(ur0, d), a1 = shfl_up(ur1, d), a2 = shfl_up(ur2, d);
+                const double b0 = shfl_down(ul0, d), b1 = shfl_down(ul1, d), b2 = shfl_down(ul2, d);
+                if (rm) {
+                    if (lane - d >= 0) { r0 -= a0; r1 -= a1; r2 -= a2; }
+                    if (lane + d < 32) { r0 -= b0; r1 -= b1; r2 -= b2; }
                 }
             }
-            // backward substitution chain  y_i = L_ii^-T (t_i - M_{i+1} y_{i+1})
-            double y0 = 0.0, y1 = 0.0, y2 = 0.0, cd0 = 0.0, cd1 = 0.0, cd2 = 0.0;
-            for (int i = n - 2; i >= 0; --i) {
-                const int src = i + 1;
-                const double u0 = shfl(cd0, src), u1 = shfl(cd1, src), u2 = shfl(cd2, src);
-                if (lane == i) {
-                    const double rr0 = t0 - u0, rr1 = t1 - u1, rr2 = t2 - u2;
-                    y2 = rr2 * F.i22;
-                    y1 = (rr1 - F.l21 * y2) * F.i11;
-                    y0 = ((rr0 - F.l10 * y1) - F.l20 * y2) * F.i00;
-                    cd0 = (F.m[0] * y0 + F.m[1] * y1) + F.m[2] * y2;
-                    cd1 = (F.m[3] * y0 + F.m[4] * y1) + F.m[5] * y2;
-                    cd2 = (F.m[6] * y0 + F.m[7] * y1) + F.m[8] * y2;
+            // back substitution, top level first: y_i = L_i^-T (t_i - XL y_{i-d} - XR y_{i+d})
+            double y0 = 0.0, y1 = 0.0, y2 = 0.0;
+            EMP_UNROLL
+            for (int lev = EMP_CR_LEVELS - 1; lev >= 0; --lev) {
+                const int d = 1 << lev, msk = 2 * d - 1;
+                const bool el = (lane & msk) == d - 1;
+                double a0 = shfl_up(y0, d), a1 = shfl_up(y1, d), a2 = shfl_up(y2, d);
+                double b0 = shfl_down(y0, d), b1 = shfl_down(y1, d), b2 = shfl_down(y2, d);
+                if (lane - d < 0) { a0 = 0.0; a1 = 0.0; a2 = 0.0; }
+                if (lane + d >= 32) { b0 = 0.0; b1 = 0.0; b2 = 0.0; }
+                if (el) {
+                    const double v0 = t0 - (((F.xl[0] * a0 + F.xl[1] * a1) + F.xl[2] * a2) + ((F.xr[0] * b0 + F.xr[1] * b1) + F.xr[2] * b2));
+                    const double v1 = t1 - (((F.xl[3] * a0 + F.xl[4] * a1) + F.xl[5] * a2) + ((F.xr[3] * b0 + F.xr[4] * b1) + F.xr[5] * b2));
+                    const double v2 = t2 - (((F.xl[6] * a0 + F.xl[7] * a1) + F.xl[8] * a2) + ((F.xr[6] * b0 + F.xr[7] * b1) + F.xr[8] * b2));
+                    y2 = v2 * F.i22;
+                    y1 = (v1 - F.l21 * y2) * F.i11;
+                    y0 = ((v0 - F.l10 * y1) - F.l20 * y2) * F.i00;
                 }
             }
             if (!stage) { y0 = 0.0; y1 = 0.0; y2 = 0.0; }
