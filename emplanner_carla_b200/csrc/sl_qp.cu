@@ -203,17 +203,18 @@ sl_qp_kernel(const double *__restrict__ scenes, double *__restrict__ plans, doub
         const double hU = shfl(lmax, min(lane + fi, n - 1));     // l_max[index1] (:130)
         const double hL = shfl(lmin, max(lane - bi, 0));         // l_min[index2] (:131)
         const double hw = Q.host_w / 2;
-        double h[NR];
-        h[0] = hU - hw; h[1] = hU + hw; h[2] = hU - hw; h[3] = hU + hw;
-        h[4] = -hL + hw; h[5] = -hL - hw; h[6] = -hL + hw; h[7] = -hL - hw;
+        // h is recomputed from 5 registers where it is needed (:133-166): rows 0-7 from the corridor, rows 8-13
+        // from the +-1e5 boxes, pinned to the plan start on lane 0 (:148-153) and to 0 on lane n-1 (:155-160)
+        const double hq[4] = {hU - hw, hU + hw, -hL + hw, -hL - hw};
+        double ubv[3];
         EMP_UNROLL
-        for (int c = 0; c < 3; ++c) {
-            double ub = 100000.0, nlb = 100000.0;                // :145-147
-            if (lane == 0) { ub = st[c]; nlb = -st[c]; }         // :148-153
-            if (lane == n - 1) { ub = 0.0; nlb = 0.0; }          // :155-160
-            h[8 + c] = ub;
-            h[11 + c] = nlb;
-        }
+        for (int c = 0; c < 3; ++c) ubv[c] = lane == 0 ? st[c] : (lane == n - 1 ? 0.0 : 100000.0);
+        const bool interior = lane != 0 && lane != n - 1;
+        auto hrow = [&](int r) -> double {
+            if (r < 8) return hq[((r >> 2) << 1) | (r & 1)];
+            if (r < 11) return ubv[r - 8];
+            return interior ? 100000.0 : -ubv[r - 11];
+        };
         // P (diagonal part) with and without the jerk terms; cc = coupling ddl_i <-> ddl_{i+1}
         double Pd[3], Pn[3];
         Pd[0] = 2 * (Q.w_l + Q.w_centre);
@@ -299,7 +300,7 @@ sl_qp_kernel(const double *__restrict__ scenes, double *__restrict__ plans, doub
             }
             if (!stage) { D00 = 1.0; D10 = 0.0; D11 = 1.0; D20 = 0.0; D21 = 0.0; D22 = 1.0; }
             bool bad = false;
-            EMP_UNROLL
+#pragma unroll 1
             for (int lev = 0; lev < EMP_CR_LEVELS; ++lev) {
                 const int d = 1 << lev, msk = 2 * d - 1;
                 const bool el = (lane & msk) == d - 1;
@@ -382,7 +383,7 @@ sl_qp_kernel(const double *__restrict__ scenes, double *__restrict__ plans, doub
             // forward elimination, level by level: t_i = L_i^-1 r_i, then r_{i-d} -= XL' t_i, r_{i+d} -= XR' t_i
             if (!stage) { r0 = 0.0; r1 = 0.0; r2 = 0.0; }
             double t0 = 0.0, t1 = 0.0, t2 = 0.0;
-            EMP_UNROLL
+#pragma unroll 1
             for (int lev = 0; lev < EMP_CR_LEVELS; ++lev) {
                 const int d = 1 << lev, msk = 2 * d - 1;
                 const bool el = (lane & msk) == d - 1;
@@ -408,7 +409,7 @@ sl_qp_kernel(const double *__restrict__ scenes, double *__restrict__ plans, doub
             }
             // back substitution, top level first: y_i = L_i^-T (t_i - XL y_{i-d} - XR y_{i+d})
             double y0 = 0.0, y1 = 0.0, y2 = 0.0;
-            EMP_UNROLL
+#pragma unroll 1
             for (int lev = EMP_CR_LEVELS - 1; lev >= 0; --lev) {
                 const int d = 1 << lev, msk = 2 * d - 1;
                 const bool el = (lane & msk) == d - 1;
@@ -460,147 +461,130 @@ sl_qp_kernel(const double *__restrict__ scenes, double *__restrict__ plans, doub
             o[2] = (G.b * yy[0] + G.e * yy[1]) + (G.g0 * p0 + G.e * p1);
         };
 
-        // ---------------- initial point (coneqp: W = I) --------------------------
+        // ---------------- coneqp iteration -----------------------------------------
+        // One loop body serves the initial point (it == -1: W = I, one solve) and the Mehrotra iterations
+        // (two solves), so factor() and kkt_solve() are instantiated once (code size: instruction cache).
+        // Per-row state: s, z live in registers; 1/s, 1/z, rz and the predictor's ds o dz live in shared
+        // memory ([row][lane], conflict-free); everything else per row is recomputed where it is used.
+        extern __shared__ double qp_smem[];
+        double *sm_is = qp_smem + (size_t)(threadIdx.x >> 5) * (4 * NR * 32) + lane;
+        double *sm_iz = sm_is + NR * 32, *sm_rz = sm_iz + NR * 32, *sm_ws = sm_rz + NR * 32;
         double s[NR], z[NR], y[2] = {0.0, 0.0};
-        {
-            double w1[NR];
-            EMP_UNROLL
-            for (int r = 0; r < NR; ++r) w1[r] = 1.0;
-            factor(w1);
-            double g[3], gth[3], by[2] = {0.0, 0.0};
-            gtmul(h, G, gth);
-            g[0] = -q0 + gth[0];
-            g[1] = gth[1];
-            g[2] = gth[2];
-            if (!valid) { g[0] = g[1] = g[2] = 0.0; }
-            kkt_solve(g, by, x, y);
-            double gx[NR];
-            gmul(x, G, gx);
-            double red[2] = {0.0, 0.0};
-            double mn_s = -1e300, mn_z = -1e300;                   // max(-s), max(-z)
-            EMP_UNROLL
-            for (int r = 0; r < NR; ++r) {
-                z[r] = valid ? gx[r] - h[r] : 1.0;
-                s[r] = valid ? -z[r] : 1.0;
-                if (valid) {
-                    red[0] += s[r] * s[r];
-                    mn_s = fmax(mn_s, -s[r]);
-                    mn_z = fmax(mn_z, -z[r]);
-                }
-            }
-            warp_sum_n(red);
-            const double nrm = sqrt(red[0]);                       // ||s|| == ||z||
-            const double ts = warp_max(mn_s), tz = warp_max(mn_z);
-            if (ts >= -1e-8 * fmax(nrm, 1.0)) {
-                EMP_UNROLL
-                for (int r = 0; r < NR; ++r) s[r] = valid ? s[r] + (1.0 + ts) : 1.0;
-            }
-            if (tz >= -1e-8 * fmax(nrm, 1.0)) {
-                EMP_UNROLL
-                for (int r = 0; r < NR; ++r) z[r] = valid ? z[r] + (1.0 + tz) : 1.0;
-            }
-            double gs = 0.0;
-            EMP_UNROLL
-            for (int r = 0; r < NR; ++r) gs += valid ? s[r] * z[r] : 0.0;
-            gap = warp_sum(gs);
-        }
-        double n0[2] = {valid ? q0 * q0 : 0.0, 0.0};
+        double rx[3] = {0.0, 0.0, 0.0}, ry[2] = {0.0, 0.0};
         EMP_UNROLL
-        for (int r = 0; r < NR; ++r) n0[1] += valid ? h[r] * h[r] : 0.0;
-        warp_sum_n(n0);
-        const double resx0 = fmax(1.0, sqrt(n0[0]));
+        for (int r = 0; r < NR; ++r) { s[r] = 1.0; z[r] = 1.0; sm_ws[r * 32] = 0.0; sm_rz[r * 32] = 0.0; }
+        double resx0 = 1.0, resz0 = 1.0, gap_limit = 0.0;
         const double resy0 = 1.0;                                  // b = 0
-        const double resz0 = fmax(1.0, sqrt(n0[1]));
-        if (broke) qp_status = EMP_QP_UNKNOWN_NUMERIC;             // cvxopt raises ValueError here
-        const double gap_limit = 100.0 * gap;                      // see "divergence exit" below
-
-        // ---------------- main loop ----------------------------------------------
-        double ws3[NR];
-        while (qp_status == EMP_QP_OK) {
-            double rx[3], ry[2], rz[NR];
-            double pxq[3], aty[3], gtz[3], gx[NR];
-            pmul(x, pxq);
-            pxq[0] += q0;
-            atmul(y, aty);
-            gtmul(z, G, gtz);
-            amul(x, ry);
-            gmul(x, G, gx);
-            double red[7] = {0, 0, 0, 0, 0, 0, 0};
-            EMP_UNROLL
-            for (int c = 0; c < 3; ++c) {
-                rx[c] = valid ? (pxq[c] + aty[c]) + gtz[c] : 0.0;
-                red[0] += rx[c] * rx[c];
-                red[3] += valid ? x[c] * pxq[c] : 0.0;
-            }
-            red[4] = valid ? x[0] * q0 : 0.0;
-            red[1] = ry[0] * ry[0] + ry[1] * ry[1];
-            red[5] = y[0] * ry[0] + y[1] * ry[1];
-            EMP_UNROLL
-            for (int r = 0; r < NR; ++r) {
-                rz[r] = valid ? (s[r] + gx[r]) - h[r] : 0.0;
-                red[2] += rz[r] * rz[r];
-                red[6] += valid ? z[r] * rz[r] : 0.0;
-            }
-            warp_sum_n(red);
-            const double resx = sqrt(red[0]), resy = sqrt(red[1]), resz = sqrt(red[2]);
-            const double pcost = 0.5 * (red[3] + red[4]);
-            const double dcost = ((pcost + red[5]) + red[6]) - gap;
-            bool have_rel = true;
-            double relgap = 0.0;
-            if (pcost < 0.0) relgap = gap / -pcost;
-            else if (dcost > 0.0) relgap = gap / dcost;
-            else have_rel = false;
-            const double pres = fmax(resy / resy0, resz / resz0);
-            const double dres = resx / resx0;
-            if (pres <= Q.feastol && dres <= Q.feastol && (gap <= Q.abstol || (have_rel && relgap <= Q.reltol))) break;
-            if (iters == Q.maxiters) { qp_status = EMP_QP_UNKNOWN_MAXITER; break; }
-            if (!isfinite((gap + resx) + resz)) { qp_status = EMP_QP_UNKNOWN_NUMERIC; break; }
-            // Divergence exit: on an infeasible corridor coneqp has no certificate; cvxopt iterates until its
-            // Cholesky breaks down or maxiters and reports 'unknown'.  The gap of a converging solve never grows
-            // above its initial value, so a gap 100x the initial one ends the solve with the same 'unknown'.
-            if (iters > 0 && gap > gap_limit) { qp_status = EMP_QP_UNKNOWN_NUMERIC; break; }
-
-            double is[NR], iz[NR], w[NR];
-            EMP_UNROLL
-            for (int r = 0; r < NR; ++r) {
-                is[r] = 1.0 / s[r];
-                iz[r] = 1.0 / z[r];
-                w[r] = z[r] * is[r];
-            }
-            factor(w);
-            if (broke) { qp_status = EMP_QP_UNKNOWN_NUMERIC; break; }   // cvxopt: ArithmeticError -> 'unknown'
-
-            const double mu = gap / (double)m_rows;
-            double sigma = 0.0, step = 1.0;
-            double dx[3], dy[2], dsv[NR], dz[NR];
-            EMP_UNROLL
-            for (int pass = 0; pass < 2; ++pass) {
-                double tq[NR], gtq[3], g[3], by[2];
+        int it = -1;
+        while (true) {
+            if (it >= 0) {
+                double pxq[3], aty[3], gtz[3], gx[NR];
+                pmul(x, pxq);
+                pxq[0] += q0;
+                atmul(y, aty);
+                gtmul(z, G, gtz);
+                amul(x, ry);
+                gmul(x, G, gx);
+                double red[7] = {0, 0, 0, 0, 0, 0, 0};
+                EMP_UNROLL
+                for (int c = 0; c < 3; ++c) {
+                    rx[c] = valid ? (pxq[c] + aty[c]) + gtz[c] : 0.0;
+                    red[0] += rx[c] * rx[c];
+                    red[3] += valid ? x[c] * pxq[c] : 0.0;
+                }
+                red[4] = valid ? x[0] * q0 : 0.0;
+                red[1] = ry[0] * ry[0] + ry[1] * ry[1];
+                red[5] = y[0] * ry[0] + y[1] * ry[1];
                 EMP_UNROLL
                 for (int r = 0; r < NR; ++r) {
-                    double bs = sigma * mu - s[r] * z[r];
-                    if (pass == 1) bs -= ws3[r];
-                    tq[r] = valid ? (bs + z[r] * rz[r]) * is[r] : 0.0;
+                    const double rzr = valid ? (s[r] + gx[r]) - hrow(r) : 0.0;
+                    sm_rz[r * 32] = rzr;
+                    red[2] += rzr * rzr;
+                    red[6] += valid ? z[r] * rzr : 0.0;
                 }
-                gtmul(tq, G, gtq);
+                warp_sum_n(red);
+                const double resx = sqrt(red[0]), resy = sqrt(red[1]), resz = sqrt(red[2]);
+                const double pcost = 0.5 * (red[3] + red[4]);
+                const double dcost = ((pcost + red[5]) + red[6]) - gap;
+                bool have_rel = true;
+                double relgap = 0.0;
+                if (pcost < 0.0) relgap = gap / -pcost;
+                else if (dcost > 0.0) relgap = gap / dcost;
+                else have_rel = false;
+                const double pres = fmax(resy / resy0, resz / resz0);
+                const double dres = resx / resx0;
+                if (pres <= Q.feastol && dres <= Q.feastol && (gap <= Q.abstol || (have_rel && relgap <= Q.reltol))) break;
+                if (it == Q.maxiters) { qp_status = EMP_QP_UNKNOWN_MAXITER; break; }
+                if (!isfinite((gap + resx) + resz)) { qp_status = EMP_QP_UNKNOWN_NUMERIC; break; }
+                // Divergence exit: on an infeasible corridor coneqp has no certificate; cvxopt iterates until its
+                // Cholesky breaks down or maxiters and reports 'unknown'.  The gap of a converging solve never
+                // grows above its initial value, so a gap 100x the initial one ends the solve with 'unknown' too.
+                if (it > 0 && gap > gap_limit) { qp_status = EMP_QP_UNKNOWN_NUMERIC; break; }
+            }
+
+            {
+                double w[NR];
                 EMP_UNROLL
-                for (int c = 0; c < 3; ++c) g[c] = -rx[c] - gtq[c];
-                by[0] = -ry[0];
-                by[1] = -ry[1];
+                for (int r = 0; r < NR; ++r) {
+                    const double isr = 1.0 / s[r];
+                    sm_is[r * 32] = isr;
+                    sm_iz[r * 32] = 1.0 / z[r];
+                    w[r] = z[r] * isr;
+                }
+                factor(w);
+            }
+            if (broke) { qp_status = EMP_QP_UNKNOWN_NUMERIC; break; }   // cvxopt: ValueError (init) / ArithmeticError
+
+            const double mu = gap / (double)m_rows;
+            const int npass = it < 0 ? 1 : 2;
+            double sigma = 0.0, step = 1.0;
+            double dx[3], dy[2];
+#pragma unroll 1
+            for (int pass = 0; pass < npass; ++pass) {
+                double g[3], by[2];
+                if (it < 0) {
+                    double gth[3], hh[NR];
+                    EMP_UNROLL
+                    for (int r = 0; r < NR; ++r) hh[r] = hrow(r);
+                    gtmul(hh, G, gth);                             // rhs of the initial point: -q + G'h, b = 0
+                    g[0] = valid ? -q0 + gth[0] : 0.0;
+                    g[1] = valid ? gth[1] : 0.0;
+                    g[2] = valid ? gth[2] : 0.0;
+                    by[0] = 0.0;
+                    by[1] = 0.0;
+                } else {
+                    double tq[NR], gtq[3];
+                    const double sm_ = sigma * mu;
+                    EMP_UNROLL
+                    for (int r = 0; r < NR; ++r) {
+                        const double bs = (sm_ - s[r] * z[r]) - (pass == 1 ? sm_ws[r * 32] : 0.0);
+                        tq[r] = valid ? (bs + z[r] * sm_rz[r * 32]) * sm_is[r * 32] : 0.0;
+                    }
+                    gtmul(tq, G, gtq);
+                    EMP_UNROLL
+                    for (int c = 0; c < 3; ++c) g[c] = -rx[c] - gtq[c];
+                    by[0] = -ry[0];
+                    by[1] = -ry[1];
+                }
                 kkt_solve(g, by, dx, dy);
+                if (it < 0) break;
                 double gdx[NR];
                 gmul(dx, G, gdx);
                 double dsdz = 0.0, ts = -1e300, tz = -1e300;
+                const double sm_ = sigma * mu;
                 EMP_UNROLL
                 for (int r = 0; r < NR; ++r) {
-                    dz[r] = tq[r] + w[r] * gdx[r];
-                    dsv[r] = -rz[r] - gdx[r];
+                    const double isr = sm_is[r * 32], rzr = sm_rz[r * 32];
+                    const double bs = (sm_ - s[r] * z[r]) - (pass == 1 ? sm_ws[r * 32] : 0.0);
+                    const double tqr = (bs + z[r] * rzr) * isr;
+                    const double dzr = tqr + (z[r] * isr) * gdx[r];
+                    const double dsr = -rzr - gdx[r];
                     if (valid) {
-                        dsdz += dsv[r] * dz[r];
-                        ts = fmax(ts, -dsv[r] * is[r]);
-                        tz = fmax(tz, -dz[r] * iz[r]);
+                        dsdz += dsr * dzr;
+                        ts = fmax(ts, -dsr * isr);
+                        tz = fmax(tz, -dzr * sm_iz[r * 32]);
                     }
-                    if (pass == 0) ws3[r] = dsv[r] * dz[r];
+                    if (pass == 0) sm_ws[r * 32] = dsr * dzr;
                 }
                 dsdz = warp_sum(dsdz);
                 const double t = fmax(0.0, warp_max(fmax(ts, tz)));
@@ -611,22 +595,72 @@ sl_qp_kernel(const double *__restrict__ scenes, double *__restrict__ plans, doub
                     sigma = (sg * sg) * sg;
                 }
             }
-            EMP_UNROLL
-            for (int c = 0; c < 3; ++c) x[c] += step * dx[c];
-            y[0] += step * dy[0];
-            y[1] += step * dy[1];
-            double gs = 0.0;
-            EMP_UNROLL
-            for (int r = 0; r < NR; ++r) {
-                if (valid) {
-                    s[r] += step * dsv[r];
-                    z[r] += step * dz[r];
-                    gs += s[r] * z[r];
+            if (it < 0) {
+                // initial point (coneqp, W = I): x, y from the solve; z = Gx - h, s = -z, shifted into the cone
+                x[0] = dx[0]; x[1] = dx[1]; x[2] = dx[2];
+                y[0] = dy[0]; y[1] = dy[1];
+                double gx[NR];
+                gmul(x, G, gx);
+                double red[3] = {0.0, valid ? q0 * q0 : 0.0, 0.0};
+                double mn_s = -1e300, mn_z = -1e300;               // max(-s), max(-z)
+                EMP_UNROLL
+                for (int r = 0; r < NR; ++r) {
+                    const double hr = hrow(r);
+                    z[r] = valid ? gx[r] - hr : 1.0;
+                    s[r] = valid ? -z[r] : 1.0;
+                    if (valid) {
+                        red[0] += s[r] * s[r];
+                        red[2] += hr * hr;
+                        mn_s = fmax(mn_s, -s[r]);
+                        mn_z = fmax(mn_z, -z[r]);
+                    }
                 }
+                warp_sum_n(red);
+                const double nrm = sqrt(red[0]);                   // ||s|| == ||z||
+                resx0 = fmax(1.0, sqrt(red[1]));
+                resz0 = fmax(1.0, sqrt(red[2]));
+                const double ts = warp_max(mn_s), tz = warp_max(mn_z);
+                const double sh_s = ts >= -1e-8 * fmax(nrm, 1.0) ? 1.0 + ts : 0.0;
+                const double sh_z = tz >= -1e-8 * fmax(nrm, 1.0) ? 1.0 + tz : 0.0;
+                double gs = 0.0;
+                EMP_UNROLL
+                for (int r = 0; r < NR; ++r) {
+                    if (valid) {
+                        if (sh_s != 0.0) s[r] += sh_s;
+                        if (sh_z != 0.0) z[r] += sh_z;
+                        gs += s[r] * z[r];
+                    }
+                }
+                gap = warp_sum(gs);
+                gap_limit = 100.0 * gap;
+            } else {
+                // step: recompute ds, dz of the corrector pass row by row (cheaper than keeping 28 registers)
+                double gdx[NR];
+                gmul(dx, G, gdx);
+                const double sm_ = sigma * mu;
+                double gs = 0.0;
+                EMP_UNROLL
+                for (int r = 0; r < NR; ++r) {
+                    const double isr = sm_is[r * 32], rzr = sm_rz[r * 32];
+                    const double bs = (sm_ - s[r] * z[r]) - sm_ws[r * 32];
+                    const double tqr = (bs + z[r] * rzr) * isr;
+                    const double dzr = tqr + (z[r] * isr) * gdx[r];
+                    const double dsr = -rzr - gdx[r];
+                    if (valid) {
+                        s[r] += step * dsr;
+                        z[r] += step * dzr;
+                        gs += s[r] * z[r];
+                    }
+                }
+                EMP_UNROLL
+                for (int c = 0; c < 3; ++c) x[c] += step * dx[c];
+                y[0] += step * dy[0];
+                y[1] += step * dy[1];
+                gap = warp_sum(gs);
             }
-            gap = warp_sum(gs);
-            ++iters;
+            ++it;
         }
+        iters = it < 0 ? 0 : it;
     }
 
     // ---------------- outputs ----------------------------------------------------
@@ -664,7 +698,9 @@ cudaError_t launch_sl_qp(const double *scenes, double *plans, double *lmin_lmax,
                          const double *lmax_in, const double *start_in, double *out_x, int32_t *status_iters,
                          const QpLaunch &p, cudaStream_t st) {
     const int grid = (p.batch + QP_WARPS - 1) / QP_WARPS;
-    sl_qp_kernel<<<grid, QP_WARPS * 32, 0, st>>>(scenes, plans, lmin_lmax, lmin_in, lmax_in, start_in, out_x,
+    const size_t smem = (size_t)QP_WARPS * 4 * NR * 32 * sizeof(double);
+    cudaFuncSetAttribute(sl_qp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    sl_qp_kernel<<<grid, QP_WARPS * 32, smem, st>>>(scenes, plans, lmin_lmax, lmin_in, lmax_in, start_in, out_x,
                                                  status_iters, p);
     return cudaGetLastError();
 }
