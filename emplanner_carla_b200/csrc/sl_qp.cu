@@ -75,6 +75,25 @@ __device__ __forceinline__ int warp_argmin(double v, int lane) {
     return idx;
 }
 
+// 1/x and 1/sqrt(x) for positive, normal-range x: hardware seed + two Newton steps (no special-case paths).
+__device__ __forceinline__ double frcp(double x) {
+    double y;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    double e = fma(-x, y, 1.0);
+    y = fma(y, e, y);
+    e = fma(-x, y, 1.0);
+    return fma(y, e, y);
+}
+__device__ __forceinline__ double frsqrt(double x) {
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    const double hx = 0.5 * x;
+    double e = fma(-hx * y, y, 0.5);
+    y = fma(y, e, y);
+    e = fma(-hx * y, y, 0.5);
+    return fma(y, e, y);
+}
+
 struct Factor {                 // per-lane pieces of the KKT factorisation
     double q00, q01, q11, q22;  // Q upper triangular, S_i^-1 = Q Q'
     double l10, l20, l21;       // strict lower part of the Cholesky factor L of this stage's pivot block
@@ -248,12 +267,12 @@ sl_qp_kernel(const double *__restrict__ scenes, double *__restrict__ plans, doub
             const double r00sq = D0 + (wa + wb);
             const double dsum = G.d1 + G.d2;
             const double r11sq = D1 + (D0 * (G.d1 * G.d1 * wa + G.d2 * G.d2 * wb) + (wa * wb) * (dsum * dsum)) / r00sq;
-            const double ir00 = rsqrt(r00sq);
-            const double ir11 = rsqrt(r11sq);
+            const double ir00 = frsqrt(r00sq);
+            const double ir11 = frsqrt(r11sq);
             F.q00 = ir00;
             F.q11 = ir11;
             F.q01 = -(s01 * ir00) * (ir00 * ir11);
-            F.q22 = rsqrt(s22);
+            F.q22 = frsqrt(s22);
             if (!valid) { F.q00 = 1.0; F.q11 = 1.0; F.q01 = 0.0; F.q22 = 1.0; }
             // U = E Q, V = F Q
             const double u01 = F.q01 + G.a * F.q11, u02 = G.b * F.q22, u12 = G.e * F.q22, v02 = G.g0 * F.q22;
@@ -300,19 +319,20 @@ sl_qp_kernel(const double *__restrict__ scenes, double *__restrict__ plans, doub
             }
             if (!stage) { D00 = 1.0; D10 = 0.0; D11 = 1.0; D20 = 0.0; D21 = 0.0; D22 = 1.0; }
             bool bad = false;
+            EMP_UNROLL
+            for (int k = 0; k < 9; ++k) { F.xl[k] = 0.0; F.xr[k] = 0.0; }
 #pragma unroll 1
             for (int lev = 0; lev < EMP_CR_LEVELS; ++lev) {
                 const int d = 1 << lev, msk = 2 * d - 1;
                 const bool el = (lane & msk) == d - 1;
-                const bool rm = (lane & msk) == msk;
                 if (el) {
-                    const double j00 = rsqrt(D00);
+                    const double j00 = frsqrt(D00);
                     const double c10 = D10 * j00, c20 = D20 * j00;
                     const double t11 = D11 - c10 * c10;
-                    const double j11 = rsqrt(t11);
+                    const double j11 = frsqrt(t11);
                     const double c21 = (D21 - c20 * c10) * j11;
                     const double t22 = (D22 - c20 * c20) - c21 * c21;
-                    const double j22 = rsqrt(t22);
+                    const double j22 = frsqrt(t22);
                     bad = bad || (stage && (!(D00 > 0.0) || !(t11 > 0.0) || !(t22 > 0.0) || !isfinite(j00 + j11 + j22)));
                     F.l10 = c10; F.l20 = c20; F.l21 = c21;
                     F.i00 = j00; F.i11 = j11; F.i22 = j22;
@@ -326,33 +346,28 @@ sl_qp_kernel(const double *__restrict__ scenes, double *__restrict__ plans, doub
                         F.xr[c] = b0; F.xr[3 + c] = b1; F.xr[6 + c] = ((CR[6 + c] - c20 * b0) - c21 * b1) * j22;
                     }
                 }
-                // products of the eliminated stages, handed to the remaining neighbours element by element
-                const bool has_a = lane - d >= 0, has_b = lane + d < 32;
+                // Products of the eliminated stages, handed to the remaining neighbours element by element.
+                // No lane predicates are needed: a lane with t trailing one-bits is "remaining" at levels < t and
+                // eliminated at level t, so its D/CL/CR are dead afterwards and may be overwritten with garbage;
+                // remaining lanes only read from lanes eliminated at this level, and a missing left/right
+                // neighbour shows up as an exactly-zero coupling block (lane 31 is never a stage).
                 EMP_UNROLL
                 for (int r = 0; r < 3; ++r) {
                     EMP_UNROLL
                     for (int c = 0; c < 3; ++c) {
-                        const double plr = el ? (F.xl[r] * F.xr[c] + F.xl[3 + r] * F.xr[3 + c]) + F.xl[6 + r] * F.xr[6 + c] : 0.0;
-                        const double fa = shfl_up(plr, d);        // (XL'XR)[r][c] of lane-d
-                        const double fb = shfl_down(plr, d);      // (XL'XR)[r][c] of lane+d
-                        if (rm) {
-                            CL[3 * c + r] = has_a ? -fa : 0.0;    // K(j, j-2d) = -(XL'XR of a)'
-                            CR[3 * r + c] = has_b ? -fb : 0.0;    // K(j, j+2d) = -(XL'XR of b)
-                        }
+                        const double plr = (F.xl[r] * F.xr[c] + F.xl[3 + r] * F.xr[3 + c]) + F.xl[6 + r] * F.xr[6 + c];
+                        CL[3 * c + r] = -shfl_up(plr, d);         // K(j, j-2d) = -(XL'XR of lane j-d)'
+                        CR[3 * r + c] = -shfl_down(plr, d);       // K(j, j+2d) = -(XL'XR of lane j+d)
                         if (c <= r) {
-                            const double prr = el ? (F.xr[r] * F.xr[c] + F.xr[3 + r] * F.xr[3 + c]) + F.xr[6 + r] * F.xr[6 + c] : 0.0;
-                            const double pll = el ? (F.xl[r] * F.xl[c] + F.xl[3 + r] * F.xl[3 + c]) + F.xl[6 + r] * F.xl[6 + c] : 0.0;
-                            const double ga = shfl_up(prr, d);    // (XR'XR) of lane-d
-                            const double gb = shfl_down(pll, d);  // (XL'XL) of lane+d
-                            const double upd = (has_a ? ga : 0.0) + (has_b ? gb : 0.0);
-                            if (rm) {
-                                if (r == 0) D00 -= upd;
-                                else if (r == 1 && c == 0) D10 -= upd;
-                                else if (r == 1) D11 -= upd;
-                                else if (c == 0) D20 -= upd;
-                                else if (c == 1) D21 -= upd;
-                                else D22 -= upd;
-                            }
+                            const double prr = (F.xr[r] * F.xr[c] + F.xr[3 + r] * F.xr[3 + c]) + F.xr[6 + r] * F.xr[6 + c];
+                            const double pll = (F.xl[r] * F.xl[c] + F.xl[3 + r] * F.xl[3 + c]) + F.xl[6 + r] * F.xl[6 + c];
+                            const double upd = shfl_up(prr, d) + shfl_down(pll, d);   // (XR'XR)(j-d) + (XL'XL)(j+d)
+                            if (r == 0) D00 -= upd;
+                            else if (r == 1 && c == 0) D10 -= upd;
+                            else if (r == 1) D11 -= upd;
+                            else if (c == 0) D20 -= upd;
+                            else if (c == 1) D21 -= upd;
+                            else D22 -= upd;
                         }
                     }
                 }
@@ -387,7 +402,6 @@ sl_qp_kernel(const double *__restrict__ scenes, double *__restrict__ plans, doub
             for (int lev = 0; lev < EMP_CR_LEVELS; ++lev) {
                 const int d = 1 << lev, msk = 2 * d - 1;
                 const bool el = (lane & msk) == d - 1;
-                const bool rm = (lane & msk) == msk;
                 double ul0 = 0.0, ul1 = 0.0, ul2 = 0.0, ur0 = 0.0, ur1 = 0.0, ur2 = 0.0;
                 if (el) {
                     t0 = r0 * F.i00;
@@ -400,12 +414,10 @@ sl_qp_kernel(const double *__restrict__ scenes, double *__restrict__ plans, doub
                     ur1 = (F.xr[1] * t0 + F.xr[4] * t1) + F.xr[7] * t2;
                     ur2 = (F.xr[2] * t0 + F.xr[5] * t1) + F.xr[8] * t2;
                 }
-                const double a0 = shfl_up(ur0, d), a1 = shfl_up(ur1, d), a2 = shfl_up(ur2, d);
-                const double b0 = shfl_down(ul0, d), b1 = shfl_down(ul1, d), b2 = shfl_down(ul2, d);
-                if (rm) {
-                    if (lane - d >= 0) { r0 -= a0; r1 -= a1; r2 -= a2; }
-                    if (lane + d < 32) { r0 -= b0; r1 -= b1; r2 -= b2; }
-                }
+                // remaining lanes: r -= XR'(j-d) t(j-d) + XL'(j+d) t(j+d)   (dead values elsewhere, see factor)
+                r0 -= shfl_up(ur0, d) + shfl_down(ul0, d);
+                r1 -= shfl_up(ur1, d) + shfl_down(ul1, d);
+                r2 -= shfl_up(ur2, d) + shfl_down(ul2, d);
             }
             // back substitution, top level first: y_i = L_i^-T (t_i - XL y_{i-d} - XR y_{i+d})
             double y0 = 0.0, y1 = 0.0, y2 = 0.0;
@@ -413,10 +425,8 @@ sl_qp_kernel(const double *__restrict__ scenes, double *__restrict__ plans, doub
             for (int lev = EMP_CR_LEVELS - 1; lev >= 0; --lev) {
                 const int d = 1 << lev, msk = 2 * d - 1;
                 const bool el = (lane & msk) == d - 1;
-                double a0 = shfl_up(y0, d), a1 = shfl_up(y1, d), a2 = shfl_up(y2, d);
-                double b0 = shfl_down(y0, d), b1 = shfl_down(y1, d), b2 = shfl_down(y2, d);
-                if (lane - d < 0) { a0 = 0.0; a1 = 0.0; a2 = 0.0; }
-                if (lane + d >= 32) { b0 = 0.0; b1 = 0.0; b2 = 0.0; }
+                const double a0 = shfl_up(y0, d), a1 = shfl_up(y1, d), a2 = shfl_up(y2, d);
+                const double b0 = shfl_down(y0, d), b1 = shfl_down(y1, d), b2 = shfl_down(y2, d);
                 if (el) {
                     const double v0 = t0 - (((F.xl[0] * a0 + F.xl[1] * a1) + F.xl[2] * a2) + ((F.xr[0] * b0 + F.xr[1] * b1) + F.xr[2] * b2));
                     const double v1 = t1 - (((F.xl[3] * a0 + F.xl[4] * a1) + F.xl[5] * a2) + ((F.xr[3] * b0 + F.xr[4] * b1) + F.xr[5] * b2));
@@ -526,9 +536,9 @@ sl_qp_kernel(const double *__restrict__ scenes, double *__restrict__ plans, doub
                 double w[NR];
                 EMP_UNROLL
                 for (int r = 0; r < NR; ++r) {
-                    const double isr = 1.0 / s[r];
+                    const double isr = frcp(s[r]);
                     sm_is[r * 32] = isr;
-                    sm_iz[r * 32] = 1.0 / z[r];
+                    sm_iz[r * 32] = frcp(z[r]);
                     w[r] = z[r] * isr;
                 }
                 factor(w);
