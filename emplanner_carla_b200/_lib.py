@@ -33,6 +33,13 @@ class StParams(C.Structure):
                 ("w_obs", C.c_double)]
 
 
+class SmoothParams(C.Structure):
+    """EmpSmoothParams: smooth_reference_line keyword defaults (reference planning_utils.py:262-264)."""
+    _fields_ = [("w_smooth", C.c_double), ("w_length", C.c_double), ("w_ref", C.c_double), ("x_thre", C.c_double),
+                ("y_thre", C.c_double), ("abstol", C.c_double), ("reltol", C.c_double), ("feastol", C.c_double),
+                ("maxiters", C.c_int32), ("heading_only", C.c_int32)]
+
+
 _P = C.c_void_p
 _DPP = C.POINTER(DpParams)
 _QPP = C.POINTER(QpParams)
@@ -53,6 +60,9 @@ _SIGNATURES = {
     "emp_frenet_to_cart_dev": (C.c_int, [_P, _P, C.c_int, _P, _P, _P, _P, C.c_int, C.c_int, _P, _P, _P]),
     "emp_frenet_project_host": (C.c_int, [_P, _P, C.c_int, _P, _P, _P, C.c_int, _P, _P, _P, _P, C.c_int, _P, _P, _P, _P, _P]),
     "emp_frenet_to_cart_host": (C.c_int, [_P, _P, _P, C.c_int, _P, _P, _P, _P, C.c_int, C.c_int, _P, _P]),
+    "emp_smooth_params_default": (None, [C.POINTER(SmoothParams)]),
+    "emp_smooth_line_dev": (C.c_int, [_P, _P, C.c_int, C.c_int, C.POINTER(SmoothParams), _P, _P, _P]),
+    "emp_smooth_line_host": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, C.POINTER(SmoothParams), _P, _P]),
     "emp_st_params_default": (None, [C.POINTER(StParams)]),
     "emp_st_dp_dev": (C.c_int, [_P, C.c_int, C.c_int, C.POINTER(StParams), _P, _P, _P, _P, _P]),
     "emp_st_dp_host": (C.c_int, [_P, _P, C.c_int, C.c_int, C.POINTER(StParams), _P, _P, _P, _P]),
@@ -128,4 +138,14 @@ def st_params(reference_speed=50, w_cost_ref_speed=4000, w_cost_accel=100, w_cos
     p = StParams()
     p.reference_speed, p.w_ref_speed = float(reference_speed), float(w_cost_ref_speed)
     p.w_accel, p.w_obs = float(w_cost_accel), float(w_cost_obs)
+    return p
+
+
+def smooth_params(w_cost_smooth=0.4, w_cost_length=0.3, w_cost_ref=0.3, x_thre=0.2, y_thre=0.2,
+                  abstol=1e-7, reltol=1e-6, feastol=1e-7, maxiters=100, heading_only=False):
+    p = SmoothParams()
+    p.heading_only = 1 if heading_only else 0
+    p.w_smooth, p.w_length, p.w_ref = float(w_cost_smooth), float(w_cost_length), float(w_cost_ref)
+    p.x_thre, p.y_thre = float(x_thre), float(y_thre)
+    p.abstol, p.reltol, p.feastol, p.maxiters = float(abstol), float(reltol), float(feastol), int(maxiters)
     return p

@@ -13,7 +13,7 @@ import ctypes as C
 import numpy as np
 
 from . import _lib
-from ._lib import EmpError, dp_params, qp_params, st_params  # noqa: F401  (re-exported)
+from ._lib import EmpError, dp_params, qp_params, st_params, smooth_params  # noqa: F401  (re-exported)
 
 PLAN_HDR = 8
 SCENE_HDR = 6
@@ -241,6 +241,19 @@ class HostPlanner:
                                                       _ptr(path_l), _ptr(npath) if npath is not None else None, M, B,
                                                       _ptr(cart), _ptr(ncart)))
         return cart, ncart
+
+    # ---- reference-line smoother (K5) ----------------------------------------------------------
+    def smooth_lines(self, xy, sp, npts=None):
+        """smooth_reference_line (+ cal_heading_kappa) for a batch of polylines xy [B, M, 2].
+        Returns (out [B, M, 4] = (x, y, theta, kappa), status [B], iterations [B])."""
+        xy = np.ascontiguousarray(xy, dtype=np.float64)
+        B, M = xy.shape[0], xy.shape[1]
+        npts = None if npts is None else np.ascontiguousarray(npts, dtype=np.int32)
+        out = np.zeros((B, M, 4))
+        si = np.zeros((B, 2), dtype=np.int32)
+        _lib.check(_lib.lib().emp_smooth_line_host(self._h, _ptr(xy), _ptr(npts) if npts is not None else None, M, B,
+                                                   C.byref(sp), _ptr(out), _ptr(si)))
+        return out, si[:, 0].copy(), si[:, 1].copy()
 
     # ---- S-T speed DP (K3) --------------------------------------------------------------------
     def st_dp(self, scenes, st, want_tables=False):

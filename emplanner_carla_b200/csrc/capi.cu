@@ -9,6 +9,7 @@
 #include "sl_kernels.h"
 #include "frenet_kernels.h"
 #include "st_kernels.h"
+#include "smooth_kernels.h"
 
 namespace {
 
@@ -123,6 +124,11 @@ struct EmpPlanner {
 
 extern "C" {
 
+void emp_smooth_params_default(EmpSmoothParams *p) {
+    p->w_smooth = 0.4; p->w_length = 0.3; p->w_ref = 0.3; p->x_thre = 0.2; p->y_thre = 0.2;
+    p->abstol = 1e-7; p->reltol = 1e-6; p->feastol = 1e-7; p->maxiters = 100; p->heading_only = 0;
+}
+
 void emp_st_params_default(EmpStParams *p) {
     p->reference_speed = 50; p->w_ref_speed = 4000; p->w_accel = 100; p->w_obs = 10000000;
 }
@@ -236,6 +242,17 @@ int emp_frenet_to_cart_dev(const double *lines, const double *s_map, int n_nodes
     cudaError_t e = emp::launch_frenet_to_cart(lines, s_map, start_sl, path_s, path_l, npath, cart, ncart, L,
                                                (cudaStream_t)stream);
     return e == cudaSuccess ? 0 : fail_cuda(e, "frenet_to_cart launch");
+}
+
+int emp_smooth_line_dev(const double *xy, const int32_t *npts, int max_points, int batch, const EmpSmoothParams *p,
+                        double *out, int32_t *status_iters, void *stream) {
+    if (!p) return fail(-1, "EmpSmoothParams is NULL");
+    if (batch < 0 || max_points < 2) return fail(-2, "bad batch / max_points");
+    if (batch == 0) return 0;
+    if (!xy || !out || !status_iters) return fail(-1, "NULL argument");
+    emp::SmoothLaunch L{*p, batch, max_points, p->heading_only == 1 ? 1 : 0};
+    cudaError_t e = emp::launch_smooth(xy, npts, out, status_iters, L, (cudaStream_t)stream);
+    return e == cudaSuccess ? 0 : fail_cuda(e, "smooth launch");
 }
 
 int emp_st_dp_dev(const double *scenes, int kmax, int batch, const EmpStParams *p, double *out, double *cost_tab,
@@ -463,6 +480,32 @@ int emp_frenet_to_cart_host(EmpPlanner *pl, const double *lines, const double *s
             t.back(cart, d_cart, B * (M + 1) * 4);
             t.back(ncart, d_nc, B);
             if (t.err != cudaSuccess) return fail_cuda(t.err, "frenet_to_cart_host copy-back");
+        }
+    }
+    EMP_CK(cudaStreamSynchronize(pl->stream), "planner stream");
+    return rc;
+}
+
+int emp_smooth_line_host(EmpPlanner *pl, const double *xy, const int32_t *npts, int max_points, int batch,
+                         const EmpSmoothParams *p, double *out, int32_t *status_iters) {
+    if (!pl || !xy || !out || !status_iters) return fail(-1, "NULL argument");
+    if (batch <= 0) return batch == 0 ? 0 : fail(-2, "bad batch");
+    EMP_CK(cudaSetDevice(pl->device), "cudaSetDevice");
+    const size_t B = batch, M = max_points;
+    int rc;
+    {
+        Tmp t(pl->stream);
+        const double *d_xy = t.in(xy, B * M * 2);
+        const int32_t *d_np = t.in(npts, B);
+        double *d_out = t.out<double>(B * M * 4);
+        int32_t *d_si = t.out<int32_t>(B * 2);
+        if (t.err != cudaSuccess) return fail_cuda(t.err, "smooth_line_host staging");
+        cudaMemsetAsync(d_out, 0, B * M * 4 * sizeof(double), pl->stream);
+        rc = emp_smooth_line_dev(d_xy, d_np, max_points, batch, p, d_out, d_si, pl->stream);
+        if (rc == 0) {
+            t.back(out, d_out, B * M * 4);
+            t.back(status_iters, d_si, B * 2);
+            if (t.err != cudaSuccess) return fail_cuda(t.err, "smooth_line_host copy-back");
         }
     }
     EMP_CK(cudaStreamSynchronize(pl->stream), "planner stream");

@@ -7,6 +7,7 @@ Reference line numbers cite planning_utils.py @ 1f115a5.  Not provided: the thre
 """
 import numpy as np
 
+from emplanner_carla_b200 import api
 from . import _runtime
 
 
@@ -81,3 +82,33 @@ def cal_s_l_deri_fun(xy_list: list, V_xy_list: list, a_xy_list: list, local_path
                                           want=("deriv",))
     d = r["deriv"][0]
     return tuple(list(d[:, k]) for k in range(7))
+
+
+def smooth_reference_line(local_frenet_path_xy: list,
+                          w_cost_smooth=0.4, w_cost_length=0.3, w_cost_ref=0.3,
+                          x_thre=0.2, y_thre=0.2):
+    """Box-constrained QP smoothing of a polyline, then heading and curvature (reference :262-361).
+    Accepts [(x, y), ...] or [(x, y, theta, kappa), ...] (and, like the reference, a first element that is
+    only (x, y)); returns [(x_opt, y_opt, theta, kappa), ...]."""
+    n = len(local_frenet_path_xy)
+    if n < 2 or n > 64:
+        raise NotImplementedError("smooth_reference_line on the GPU handles 2..64 points (got %d)" % n)
+    xy = _pts(local_frenet_path_xy)
+    sp = api.smooth_params(w_cost_smooth, w_cost_length, w_cost_ref, x_thre, y_thre)
+    out, status, iters = _runtime.planner().smooth_lines(xy, sp)
+    smooth_reference_line.last_status = (int(status[0]), int(iters[0]))
+    return [tuple(r) for r in out[0]]
+
+
+smooth_reference_line.last_status = None
+
+
+def cal_heading_kappa(frenet_path_xy_list: list):
+    """Heading and curvature of a polyline by central differences (reference :185-228).
+    Returns (theta list, kappa list)."""
+    n = len(frenet_path_xy_list)
+    if n < 2 or n > 64:
+        raise NotImplementedError("cal_heading_kappa on the GPU handles 2..64 points (got %d)" % n)
+    sp = api.smooth_params(heading_only=True)
+    out, _, _ = _runtime.planner().smooth_lines(_pts(frenet_path_xy_list), sp)
+    return list(out[0, :, 2]), list(out[0, :, 3])

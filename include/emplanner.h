@@ -79,6 +79,15 @@ typedef struct EmpStParams {          /* speed_DP, speed_planning_test.py:101-10
     double w_obs;                     /* 10000000 */
 } EmpStParams;
 
+typedef struct EmpSmoothParams {      /* smooth_reference_line, planning_utils.py:262-264 + cvxopt defaults */
+    double w_smooth, w_length, w_ref; /* 0.4, 0.3, 0.3 */
+    double x_thre, y_thre;            /* 0.2, 0.2 */
+    double abstol, reltol, feastol;   /* 1e-7, 1e-6, 1e-7 */
+    int32_t maxiters;                 /* 100 */
+    int32_t heading_only;             /* 1: skip the QP, output cal_heading_kappa (:185-228) of the input polyline */
+} EmpSmoothParams;
+
+void emp_smooth_params_default(EmpSmoothParams *p);
 void emp_st_params_default(EmpStParams *p);
 void emp_dp_params_default(EmpDpParams *p);
 void emp_qp_params_default(EmpQpParams *p);
@@ -182,6 +191,16 @@ int emp_frenet_project_host(EmpPlanner *pl, const double *lines, int n_nodes, co
 int emp_frenet_to_cart_host(EmpPlanner *pl, const double *lines, const double *s_map, int n_nodes,
                             const double *start_sl, const double *path_s, const double *path_l,
                             const int32_t *npath, int max_points, int batch, double *cart, int32_t *ncart);
+
+/* ---- reference-line smoother (K5) ----------------------------------------------------------
+ * Replaces planning_utils.smooth_reference_line (:262-361, incl. cvxopt.solvers.qp :353) and
+ * cal_heading_kappa (:185-228) for a batch of polylines, one launch.
+ * xy: [batch, max_points, 2]; npts[batch] (NULL = max_points), 2 <= n <= 64;
+ * out: [batch, max_points, 4] = (x_opt, y_opt, theta, kappa); status_iters [batch,2] like emp_qp_dev. */
+int emp_smooth_line_dev(const double *xy, const int32_t *npts, int max_points, int batch, const EmpSmoothParams *p,
+                        double *out, int32_t *status_iters, void *stream);
+int emp_smooth_line_host(EmpPlanner *pl, const double *xy, const int32_t *npts, int max_points, int batch,
+                         const EmpSmoothParams *p, double *out, int32_t *status_iters);
 
 /* ---- S-T speed DP (K3) -----------------------------------------------------------------
  * Replaces speed_planning_test.speed_DP (:101-188) with CalcDpCost (:191), CalcObsCost (:234),

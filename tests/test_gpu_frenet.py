@@ -106,3 +106,82 @@ def test_dropin_planning_utils_sequence(planner):
         sys.path.remove(pkg_dir)
         for k in [k for k in sys.modules if k == "planner" or k.startswith("planner.")]:
             del sys.modules[k]
+
+
+def test_smooth_reference_line_against_reference_golden(planner):
+    """QP#1 (51-node local line -> smoothed line with heading/curvature) and QP#3 (Cartesian path smoothing) against
+    the reference's own outputs (reference matrix construction + restated coneqp).  Tolerance 1e-6 m on x, y;
+    1e-6 rad on theta; 1e-6 1/m on kappa (the QP stops at cvxopt's default tolerances, the kernel's linear algebra
+    differs from the dense oracle's only by rounding)."""
+    from emplanner_carla_b200 import api
+    g = load_golden("frenet.npz")
+    out, status, iters = planner.smooth_lines(g["local"][:, :, :2], api.smooth_params())
+    assert np.all(status == 0)
+    assert np.abs(out[:, :, :2] - g["line"][:, :, :2]).max() < 1e-6
+    assert np.abs(out[:, :, 2] - g["line"][:, :, 2]).max() < 1e-6
+    assert np.abs(out[:, :, 3] - g["line"][:, :, 3]).max() < 1e-6
+    assert iters.min() >= 2 and iters.max() <= 8
+    # QP#3: ragged lengths (the Frenet->Cartesian output is truncated at s_map[-1])
+    F = len(g["cart_n"])
+    M = g["cart_raw"].shape[1]
+    xy = np.where(np.isnan(g["cart_raw"][:, :, :2]), 0.0, g["cart_raw"][:, :, :2])
+    out3, status3, _ = planner.smooth_lines(xy, api.smooth_params(), npts=g["cart_n"])
+    for f in range(F):
+        n = g["cart_n"][f]
+        assert status3[f] == 0
+        assert np.abs(out3[f, :n] - g["cart"][f, :n]).max() < 1e-6
+    # cal_heading_kappa alone
+    hk, _, _ = planner.smooth_lines(g["line"][:, :, :2], api.smooth_params(heading_only=True))
+    assert np.abs(hk[:, :, 2:] - g["line"][:, :, 2:]).max() < 1e-9
+
+
+def test_full_frame_pipeline_dropin(planner):
+    """test_9.motion_planning steps 1-14 with the drop-in modules only (no reference, no cvxopt)."""
+    pkg_dir = os.path.join(ROOT, "emplanner_carla_b200")
+    sys.path.insert(0, pkg_dir)
+    for k in [k for k in sys.modules if k == "planner" or k.startswith("planner.")]:
+        del sys.modules[k]
+    try:
+        from planner import path_planning, planning_utils
+        g = load_golden("frenet.npz")
+        gp = [tuple(r) for r in g["global_path"]]
+        f = 2
+        ego = tuple(g["ego"][f])
+        mi, _ = planning_utils.find_match_points([ego], gp, False, int(g["pre_idx"][f]))
+        local = planning_utils.sampling(mi[0], gp)
+        line = planning_utils.smooth_reference_line(local)
+        assert np.abs(np.array(line) - g["line"][f]).max() < 1e-6
+        s_map = planning_utils.cal_s_map_fun(line, origin_xy=ego)
+        obs_s, obs_l = planning_utils.cal_s_l_fun([tuple(p) for p in g["obs_xy"][f][:2]], line, s_map)
+        bs, bl = planning_utils.cal_s_l_fun([ego], line, s_map)
+        l_list, _, _, _, l_ds, _, l_dds = planning_utils.cal_s_l_deri_fun([ego], [tuple(g["vel"][f])], [tuple(g["acc"][f])],
+                                                                          line, ego)
+        dp_s, dp_l = path_planning.DP_algorithm(obs_s, obs_l, plan_start_s=bs[0], plan_start_l=l_list[0],
+                                                plan_start_dl=l_ds[0], plan_start_ddl=l_dds[0])
+        dp_s, dp_l = dp_s[::2], dp_l[::2]
+        l_min, l_max = path_planning.cal_lmin_lmax(dp_s, dp_l, obs_s, obs_l, 5, 5)
+        ql, qdl, qddl = path_planning.Quadratic_planning(l_min, l_max, l_list[0], l_ds[0], l_dds[0])
+        path_s = [dp_s[0]] + [(dp_s[i] + dp_s[i - 1]) / 2 for i in range(1, len(ql))] + [dp_s[-1]]
+        path_l = [ql[0]] + [(ql[i] + ql[i - 1]) / 2 for i in range(1, len(ql))] + [ql[-1]]
+        cart = path_planning.frenet_2_x_y_theta_kappa(bs[0], bl[0], path_s, path_l, line, s_map)
+        assert 10 < len(cart) <= len(path_s) + 1 and all(len(c) == 4 for c in cart)
+        assert np.hypot(cart[0][0] - ego[0], cart[0][1] - ego[1]) < 0.5      # starts at the ego position
+        # the same frame through the CPU oracle chain
+        from oracle import frenet as ofr, sl_dp, sl_qp
+        o_line, _ = ofr.smooth_reference_line(local)
+        o_smap = ofr.s_map(o_line, ego)
+        o_os, o_ol = ofr.s_l([tuple(p) for p in g["obs_xy"][f][:2]], o_line, o_smap)
+        o_bs, o_bl = ofr.s_l([ego], o_line, o_smap)
+        o_der = ofr.s_l_deriv([ego], [tuple(g["vel"][f])], [tuple(g["acc"][f])], o_line, ego)
+        o_s, o_l, _ = sl_dp.dp_algorithm(o_os, o_ol, o_bs[0], o_der[0][0], o_der[4][0], o_der[6][0])
+        o_lmin, o_lmax = sl_qp.corridor(o_s[::2], o_l[::2], o_os, o_ol, 5, 5)
+        o_ql, _, _, info = sl_qp.quadratic_planning(o_lmin, o_lmax, o_der[0][0], o_der[4][0], o_der[6][0])
+        o_ps, o_pl = sl_qp.midpoint_path(o_s[::2], o_ql)
+        o_cart = ofr.frenet_to_cartesian(o_bs[0], o_bl[0], list(o_ps), list(o_pl), o_line, o_smap)
+        assert info["status"] == "optimal" and len(o_cart) == len(cart)
+        err = np.abs(np.array(cart) - np.array(o_cart))
+        assert err[:, :2].max() < 1e-4 and err[:, 2].max() < 1e-4 and err[:, 3].max() < 1e-4, err.max(axis=0)
+    finally:
+        sys.path.remove(pkg_dir)
+        for k in [k for k in sys.modules if k == "planner" or k.startswith("planner.")]:
+            del sys.modules[k]
