@@ -34,6 +34,16 @@ UNIT = "frames/s"
 SCENE_BYTES = 164
 
 
+# Static ncu facts of the current kernels (one `ncu --set full` capture per change, see profiles/): the FP64 pipe
+# utilisation is the compute-roofline fraction; dram bytes per launch (batch 4096) go into roofline.traffic.
+NCU_STATIC = {
+    "C_60x11": {"fp64_pipe_active": {"sl_dp_kernel": 0.353, "sl_qp_kernel": 0.290},
+                "issue_active": {"sl_dp_kernel": 0.472, "sl_qp_kernel": 0.423},
+                "dram_bytes_per_launch": {"sl_dp_kernel": 842240 + 477952, "sl_qp_kernel": 5516800},
+                "source": "profiles/r1_ncu_full_v4_summary.txt (batch 4096, lattice C)"},
+}
+
+
 def algorithmic_bytes(n_enr, n_qp):
     dp = SCENE_BYTES + (4 + n_enr * 16 + 4)                      # scene in; n_enr + (s,l) + status out
     qp = SCENE_BYTES + n_qp * 16 + (n_qp * 24 + 8)               # scene + [::2] path in; (l,dl,ddl) + status out
@@ -190,6 +200,9 @@ def main():
     ap.add_argument("--cpu-frames", type=int, default=1024, help="frames of the CPU baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-flush", action="store_true", help="do not flush L2 between timed steps")
+    ap.add_argument("--gather", default="p2p", choices=["p2p", "nccl"],
+                    help="N>1: p2p = plan records stored into peers' buffers by the QP kernel (CUDA IPC, NVLink); "
+                         "nccl = one in-place NCCL all-gather after the kernels")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
 
@@ -222,7 +235,8 @@ def main():
     rec_host = api.pack_scenes(**shard)
     scenes_d = torch.from_numpy(rec_host).to(dev)
     from emplanner_carla_b200 import sharding
-    gbuf = sharding.GatherBuffer(B, stride, dev)
+    use_p2p = world > 1 and args.gather == "p2p"
+    gbuf = sharding.PeerGatherBuffer(B, stride, dev) if use_p2p else sharding.GatherBuffer(B, stride, dev)
     mine = gbuf.mine                                                   # kernels write straight into the send slice
     flush = None if args.no_flush else torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     stream = torch.cuda.current_stream()
@@ -233,11 +247,17 @@ def main():
         api.dp_device(scenes_d, dp, NE, plans=mine)
         if ev:
             ev[1].record(stream)
-        api.qp_device(scenes_d, qp, NE, mine)
+        if use_p2p:
+            api.plan_device_p2p_qp(scenes_d, qp, NE, mine, gbuf.peer_array, gbuf.n_peers)   # QP + peer stores
+        else:
+            api.qp_device(scenes_d, qp, NE, mine)
         if ev:
             ev[2].record(stream)
         if world > 1:
-            gbuf.all_gather()                                          # one in-place NCCL all-gather of plan records
+            if use_p2p:
+                gbuf.fence()                                           # 1-element all-reduce = cross-rank barrier
+            else:
+                gbuf.all_gather()                                      # one in-place NCCL all-gather of plan records
         if ev:
             ev[3].record(stream)
 
@@ -272,7 +292,10 @@ def main():
 
     # ---- end-to-end through the host-buffer C ABI (what a drop-in caller gets) --------------
     planner = api.HostPlanner(max_batch=B, kmax=8, n_enr_max=NE, max_col=lat.col, device=local)
-    out = np.empty((B, stride), dtype=np.float64)
+    out = api.pinned_empty((B, stride))                              # page-locked host buffers, like a real ingest path
+    rec_pin = api.pinned_empty(rec_host.shape)
+    rec_pin[:] = rec_host
+    rec_host = rec_pin
     for _ in range(args.warmup):
         planner.plan(rec_host, dp, qp, out=out)
     if world > 1:
@@ -314,8 +337,13 @@ def main():
     dom_bytes = (b_qp if t_qp >= t_dp else b_dp) * B
     achieved = dom_bytes / (dom_ms * 1e-3) / 1e9
     fp64_tf, _ = api.fp64_peak(8192)
-    flops = (qp_flops(n_qp, iters) if t_qp >= t_dp else dp_flops(lat, float(shard["nobs"].mean()))) * B
-    comp_ach = flops / (dom_ms * 1e-3) / 1e12
+    # Reference-equivalent FP64 work (SURVEY.md §8(d) operation counts of the *reference* algorithm) per second.
+    # It can exceed the FMA peak: the kernels skip work the reference performs (obstacle culling, closed-form
+    # quintics, a banded instead of dense KKT solve).  The roofline fraction that bounds the kernels is the FP64
+    # pipe utilisation measured by ncu (profiles/, static per round), not this number.
+    ref_flops = (dp_flops(lat, float(shard["nobs"].mean())) + 25e6) * B      # DP + dense-cvxopt QP (~25 MFLOP, §8(d))
+    ref_equiv = ref_flops / ((t_dp + t_qp) / args.steps * 1e-3) / 1e12
+    ncu = NCU_STATIC.get(lat.name, {})
 
     cpu = None
     if not args.no_cpu_baseline:
@@ -332,7 +360,9 @@ def main():
         "dtype": "f64", "data": "synthetic",
         "config": {"workload": "batch=%d/GPU synthetic Frenet scenes, %dx%d S-L lattice (%s), 0-8 random obstacles, "
                                "DP->[::2]->corridor->QP%s" % (B, lat.col, lat.row, lat.name,
-                                                               ", NCCL all-gather of plan records" if world > 1 else ""),
+                                                               (", all-gather of plan records fused into the QP kernel "
+                                                                "(P2P stores over NVLink)" if use_p2p else
+                                                                ", NCCL all-gather of plan records") if world > 1 else ""),
                    "lattice": lat.name, "batch_per_gpu": B, "global_batch": B * world,
                    "parallelism": "frame-sharded x%d" % world,
                    "l2": "flushed with a 256 MiB write between timed steps" if flush is not None else "not flushed",
@@ -340,14 +370,19 @@ def main():
         "kernels_ms": {"sl_dp_kernel": t_dp / args.steps, "sl_qp_kernel": t_qp / args.steps,
                        "collective": max(t_all - t_dp - t_qp, 0.0) / args.steps},
         "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
-                     "frac": achieved / hbm_peak, "traffic": None, "peak_source": peak_src,
+                     "frac": achieved / hbm_peak, "traffic": ncu.get("dram_bytes_per_launch", {}).get(dom),
+                     "peak_source": peak_src,
                      "algorithmic_bytes_per_frame": (b_qp if t_qp >= t_dp else b_dp),
                      "note": "path is FP64-latency bound, not HBM bound (SURVEY.md §0.5); see compute"},
-        "compute": {"bound": "fp64", "kernel": dom, "achieved": comp_ach, "peak": fp64_tf, "unit": "TFLOP/s",
-                    "frac": comp_ach / fp64_tf if fp64_tf else None,
-                    "peak_source": "emp_fp64_peak FMA micro-benchmark, this GPU, this run"},
+        "compute": {"bound": "fp64", "kernel": dom, "peak": fp64_tf, "unit": "TFLOP/s",
+                    "peak_source": "emp_fp64_peak FMA micro-benchmark, this GPU, this run",
+                    "fp64_pipe_active_frac": ncu.get("fp64_pipe_active"), "issue_active_frac": ncu.get("issue_active"),
+                    "ncu_source": ncu.get("source"),
+                    "reference_equivalent_tflops": ref_equiv,
+                    "note": "fraction of the FP64 roofline = ncu sm__pipe_fp64_cycles_active of the dominant kernel; "
+                            "reference_equivalent counts the reference's operation count and may exceed the peak"},
         "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": int(rec_host.nbytes),
-                "d2h_bytes_per_step": int(out.nbytes), "api": "emp_sl_plan_host via HostPlanner.plan"},
+                "d2h_bytes_per_step": int(out.nbytes), "api": "emp_sl_plan_host via HostPlanner.plan, page-locked host buffers"},
         "gpu_launches": 2 * args.steps, "collectives": (args.steps if world > 1 else 0),
         "clocks": clocks,
     }

@@ -73,6 +73,15 @@ _SIGNATURES = {
     "emp_sl_dp_host": (C.c_int, [_P, _P, C.c_int, _DPP, _P, _P]),
     "emp_qp_host": (C.c_int, [_P, _P, _P, _P, C.c_int, C.c_int, _QPP, _P, _P]),
     "emp_corridor_host": (C.c_int, [_P, _P, _P, C.c_int, _P, C.c_int, _QPP, _P, _P]),
+    "emp_sl_plan_p2p_dev": (C.c_int, [_P, C.c_int, C.c_int, _DPP, _QPP, C.c_int, _P, _P, C.c_int, _P, _P]),
+    "emp_sl_qp_p2p_dev": (C.c_int, [_P, C.c_int, C.c_int, _QPP, C.c_int, _P, C.c_int, _P, _P]),
+    "emp_device_alloc": (_P, [C.c_size_t]),
+    "emp_device_free": (None, [_P]),
+    "emp_ipc_export": (C.c_int, [_P, _P]),
+    "emp_ipc_open": (C.c_int, [_P, C.POINTER(_P)]),
+    "emp_ipc_close": (C.c_int, [_P]),
+    "emp_host_alloc": (_P, [C.c_size_t]),
+    "emp_host_free": (None, [_P]),
     "emp_planner_last_kernel_ms": (C.c_double, [_P]),
 }
 

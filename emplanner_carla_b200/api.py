@@ -126,6 +126,34 @@ def _ptr(a):
     return a.ctypes.data_as(C.c_void_p)
 
 
+class _PinnedOwner:
+    def __init__(self, ptr):
+        self.ptr = ptr
+
+    def __del__(self):
+        try:
+            _lib.lib().emp_host_free(self.ptr)
+        except Exception:
+            pass
+
+
+def pinned_empty(shape, dtype=np.float64):
+    """numpy array backed by page-locked memory (emp_host_alloc): the *_host entry points DMA directly
+    from/to such arrays instead of staging them."""
+    dtype = np.dtype(dtype)
+    n = int(np.prod(shape))
+    ptr = _lib.lib().emp_host_alloc(max(n * dtype.itemsize, 1))
+    if not ptr:
+        raise EmpError("emp_host_alloc failed: %s" % _lib.lib().emp_last_error().decode())
+    buf = (C.c_byte * (n * dtype.itemsize)).from_address(ptr)
+    arr = np.frombuffer(buf, dtype=dtype, count=n).reshape(shape)
+    _pinned_owners[arr.__array_interface__["data"][0]] = _PinnedOwner(ptr)
+    return arr
+
+
+_pinned_owners = {}
+
+
 class HostPlanner:
     """EmpPlanner handle: host buffers in, host buffers out.  CUDA is first touched here,
     never at import (the reference forks its planner process before planning, test_9.py:226-227)."""
@@ -303,6 +331,25 @@ def plan_device(scenes, dp, qp, n_enr_max, plans=None, rows=None, kmax=None):
         plans = torch.empty((B, plan_stride(n_enr_max)), dtype=torch.float64, device=scenes.device)
     _lib.check(_lib.lib().emp_sl_plan_dev(_dev_ptr(scenes), kmax, B, C.byref(dp), C.byref(qp), int(n_enr_max),
                                           _dev_ptr(plans), _dev_ptr(rows), _stream_ptr()))
+    return plans
+
+
+def plan_device_p2p(scenes, dp, qp, n_enr_max, plans, peer_array, n_peers, rows=None):
+    """plan_device + fused all-gather: each finished plan record is also stored into the peers' gather buffers
+    (peer_array: ctypes array of device pointers from sharding.PeerGatherBuffer)."""
+    B = scenes.shape[0]
+    kmax = (scenes.shape[1] - SCENE_HDR) // 2
+    _lib.check(_lib.lib().emp_sl_plan_p2p_dev(_dev_ptr(scenes), kmax, B, C.byref(dp), C.byref(qp), int(n_enr_max),
+                                              _dev_ptr(plans), _dev_ptr(rows), int(n_peers), peer_array, _stream_ptr()))
+    return plans
+
+
+def plan_device_p2p_qp(scenes, qp, n_enr_max, plans, peer_array, n_peers):
+    """The corridor+QP launch of the fused step (after dp_device), with peer stores."""
+    B = scenes.shape[0]
+    kmax = (scenes.shape[1] - SCENE_HDR) // 2
+    _lib.check(_lib.lib().emp_sl_qp_p2p_dev(_dev_ptr(scenes), kmax, B, C.byref(qp), int(n_enr_max), _dev_ptr(plans),
+                                            int(n_peers), peer_array, _stream_ptr()))
     return plans
 
 

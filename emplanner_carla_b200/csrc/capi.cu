@@ -26,6 +26,15 @@ int fail_cuda(cudaError_t e, const char *where) {
 
 inline int align_up(int v, int a) { return (v + a - 1) / a * a; }
 
+bool is_pinned(const void *p) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return a.type == cudaMemoryTypeHost;
+}
+
 int make_dp_launch(emp::DpLaunch &L, const EmpDpParams *p, int kmax, int batch, int n_enr_max) {
     if (!p) return fail(-1, "EmpDpParams is NULL");
     if (p->row < 1 || p->row > EMP_MAX_ROW) return fail(-2, "row must be in [1, 16]");
@@ -79,6 +88,8 @@ int make_qp_launch(emp::QpLaunch &L, const EmpQpParams *p, int kmax, int batch, 
     L.n_enr_max = n_enr_max;
     L.n_direct = n_direct;
     L.mode = mode;
+    L.n_peers = 0;
+    for (int r = 0; r < EMP_MAX_PEERS; ++r) L.peer[r] = nullptr;
     return 0;
 }
 
@@ -267,6 +278,69 @@ int emp_st_dp_dev(const double *scenes, int kmax, int batch, const EmpStParams *
     return e == cudaSuccess ? 0 : fail_cuda(e, "st_dp launch");
 }
 
+int emp_sl_qp_p2p_dev(const double *scenes, int kmax, int batch, const EmpQpParams *qp, int n_enr_max,
+                      double *plans, int n_peers, double *const *peer_slices, void *stream) {
+    if (n_peers < 0 || n_peers > EMP_MAX_PEERS) return fail(-2, "n_peers must be in [0, 8]");
+    if (n_peers > 0 && !peer_slices) return fail(-1, "peer_slices is NULL");
+    emp::QpLaunch L;
+    if (int rc = make_qp_launch(L, qp, kmax, batch, n_enr_max, 0, emp::QP_MODE_FUSED)) return rc;
+    if (batch == 0) return 0;
+    if (!scenes || !plans) return fail(-1, "scenes/plans is NULL");
+    L.n_peers = n_peers;
+    for (int r = 0; r < n_peers; ++r) {
+        if (!peer_slices[r]) return fail(-1, "peer slice is NULL");
+        L.peer[r] = peer_slices[r];
+    }
+    cudaError_t e = emp::launch_sl_qp(scenes, plans, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, L,
+                                      (cudaStream_t)stream);
+    return e == cudaSuccess ? 0 : fail_cuda(e, "sl_qp (p2p) launch");
+}
+
+int emp_sl_plan_p2p_dev(const double *scenes, int kmax, int batch, const EmpDpParams *dp, const EmpQpParams *qp,
+                        int n_enr_max, double *plans, int32_t *rows, int n_peers, double *const *peer_slices,
+                        void *stream) {
+    if (int rc = emp_sl_dp_dev(scenes, kmax, batch, dp, n_enr_max, plans, rows, stream)) return rc;
+    return emp_sl_qp_p2p_dev(scenes, kmax, batch, qp, n_enr_max, plans, n_peers, peer_slices, stream);
+}
+
+void *emp_device_alloc(size_t bytes) {
+    void *p = nullptr;
+    if (cudaMalloc(&p, bytes) != cudaSuccess) {
+        fail_cuda(cudaGetLastError(), "emp_device_alloc");
+        return nullptr;
+    }
+    cudaMemset(p, 0, bytes);
+    return p;
+}
+
+void emp_device_free(void *p) {
+    if (p) cudaFree(p);
+}
+
+int emp_ipc_export(const void *dev_ptr, unsigned char handle[64]) {
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "handle size");
+    if (!dev_ptr || !handle) return fail(-1, "NULL argument");
+    cudaIpcMemHandle_t h;
+    cudaError_t e = cudaIpcGetMemHandle(&h, const_cast<void *>(dev_ptr));
+    if (e != cudaSuccess) return fail_cuda(e, "cudaIpcGetMemHandle");
+    memcpy(handle, &h, 64);
+    return 0;
+}
+
+int emp_ipc_open(const unsigned char handle[64], void **dev_ptr) {
+    if (!handle || !dev_ptr) return fail(-1, "NULL argument");
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, 64);
+    cudaError_t e = cudaIpcOpenMemHandle(dev_ptr, h, cudaIpcMemLazyEnablePeerAccess);
+    return e == cudaSuccess ? 0 : fail_cuda(e, "cudaIpcOpenMemHandle");
+}
+
+int emp_ipc_close(void *dev_ptr) {
+    if (!dev_ptr) return 0;
+    cudaError_t e = cudaIpcCloseMemHandle(dev_ptr);
+    return e == cudaSuccess ? 0 : fail_cuda(e, "cudaIpcCloseMemHandle");
+}
+
 int emp_fp64_peak(int iters, double *tflops, double *ms) {
     cudaError_t e = emp::launch_fp64_peak(iters, tflops, ms);
     return e == cudaSuccess ? 0 : fail_cuda(e, "fp64 peak");
@@ -339,9 +413,12 @@ static int plan_host_impl(EmpPlanner *pl, const double *scenes, int batch, const
     const size_t sb = (size_t)batch * emp_scene_stride(pl->kmax) * 8;
     const size_t pb = (size_t)batch * emp_plan_stride(pl->n_enr_max) * 8;
     const size_t rb = (size_t)batch * dp->col * 4;
-    // Caller buffers may be pageable: stage through pinned memory so the copies are truly asynchronous DMA.
-    memcpy(pl->h_scenes, scenes, sb);
-    EMP_CK(cudaMemcpyAsync(pl->d_scenes, pl->h_scenes, sb, cudaMemcpyHostToDevice, pl->stream), "H2D scenes");
+    // Pageable caller buffers are staged through the planner's pinned buffers so the copies are real DMA;
+    // buffers that are already page-locked (emp_host_alloc, cudaHostRegister, torch pin_memory) are used directly.
+    const bool in_pinned = is_pinned(scenes), out_pinned = is_pinned(plans), rows_pinned = rows && is_pinned(rows);
+    const double *h_in = scenes;
+    if (!in_pinned) { memcpy(pl->h_scenes, scenes, sb); h_in = pl->h_scenes; }
+    EMP_CK(cudaMemcpyAsync(pl->d_scenes, h_in, sb, cudaMemcpyHostToDevice, pl->stream), "H2D scenes");
     EMP_CK(cudaEventRecord(pl->ev0, pl->stream), "event");
     int rc = emp_sl_dp_dev(pl->d_scenes, pl->kmax, batch, dp, pl->n_enr_max, pl->d_plans, rows ? pl->d_rows : nullptr, pl->stream);
     if (rc) return rc;
@@ -350,11 +427,11 @@ static int plan_host_impl(EmpPlanner *pl, const double *scenes, int batch, const
         if (rc) return rc;
     }
     EMP_CK(cudaEventRecord(pl->ev1, pl->stream), "event");
-    EMP_CK(cudaMemcpyAsync(pl->h_plans, pl->d_plans, pb, cudaMemcpyDeviceToHost, pl->stream), "D2H plans");
-    if (rows) EMP_CK(cudaMemcpyAsync(pl->h_rows, pl->d_rows, rb, cudaMemcpyDeviceToHost, pl->stream), "D2H rows");
+    EMP_CK(cudaMemcpyAsync(out_pinned ? plans : pl->h_plans, pl->d_plans, pb, cudaMemcpyDeviceToHost, pl->stream), "D2H plans");
+    if (rows) EMP_CK(cudaMemcpyAsync(rows_pinned ? rows : pl->h_rows, pl->d_rows, rb, cudaMemcpyDeviceToHost, pl->stream), "D2H rows");
     EMP_CK(cudaStreamSynchronize(pl->stream), "planner stream");
-    memcpy(plans, pl->h_plans, pb);
-    if (rows) memcpy(rows, pl->h_rows, rb);
+    if (!out_pinned) memcpy(plans, pl->h_plans, pb);
+    if (rows && !rows_pinned) memcpy(rows, pl->h_rows, rb);
     cudaEventElapsedTime(&pl->last_ms, pl->ev0, pl->ev1);
     return 0;
 }
@@ -542,6 +619,19 @@ int emp_st_dp_host(EmpPlanner *pl, const double *scenes, int kmax, int batch, co
     EMP_CK(cudaStreamSynchronize(pl->stream), "planner stream");
     cudaEventElapsedTime(&pl->last_ms, pl->ev0, pl->ev1);
     return rc;
+}
+
+void *emp_host_alloc(size_t bytes) {
+    void *p = nullptr;
+    if (cudaMallocHost(&p, bytes) != cudaSuccess) {
+        fail_cuda(cudaGetLastError(), "emp_host_alloc");
+        return nullptr;
+    }
+    return p;
+}
+
+void emp_host_free(void *p) {
+    if (p) cudaFreeHost(p);
 }
 
 double emp_planner_last_kernel_ms(const EmpPlanner *pl) { return pl ? (double)pl->last_ms : 0.0; }

@@ -36,6 +36,8 @@ struct QpLaunch {
     int batch, kmax, scene_stride, plan_stride, n_enr_max;
     int n_direct;             // stations per frame in the DIRECT / CORRIDOR modes
     int mode;                 // QP_MODE_*
+    int n_peers;              // fused all-gather: number of peer slices to push each plan record to
+    double *peer[EMP_MAX_PEERS];
 };
 
 cudaError_t launch_sl_dp(const double *scenes, double *plans, int32_t *rows, const DpLaunch &p, cudaStream_t st);

@@ -688,6 +688,22 @@ sl_qp_kernel(const double *__restrict__ scenes, double *__restrict__ plans, doub
             plan[4] = (double)iters;
             plan[6] = gap;
         }
+        if (p.n_peers > 0) {
+            // Fused all-gather: push the finished plan record into every peer's gather buffer with 16-byte
+            // stores over NVLink (peer pointers opened through CUDA IPC); the transfers of finished frames overlap
+            // the solves still running on this GPU.  A stream-ordered barrier after the launch makes them visible.
+            __syncwarp();
+            const double2 *src = reinterpret_cast<const double2 *>(plan);
+            const int words2 = p.plan_stride >> 1;
+            for (int w = lane; w < words2; w += 32) {
+                const double2 vv = src[w];
+#pragma unroll 1
+                for (int r = 0; r < p.n_peers; ++r) {
+                    double2 *dst = reinterpret_cast<double2 *>(p.peer[r] + (size_t)frame * p.plan_stride);
+                    dst[w] = vv;
+                }
+            }
+        }
     } else {
         if (lane < n && n <= EMP_MAX_QP_POINTS) {
             double *o = out_x + (size_t)frame * 3 * n;

@@ -22,6 +22,7 @@
 #ifndef EMPLANNER_H_
 #define EMPLANNER_H_
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -33,6 +34,7 @@ extern "C" {
 #define EMP_MAX_ROW 16           /* lattice rows supported by the DP kernel */
 #define EMP_MAX_KMAX 32          /* obstacle slots per scene record */
 #define EMP_MAX_QP_POINTS 32     /* QP stations per frame (one warp lane each) */
+#define EMP_MAX_PEERS 8          /* GPUs of one NVSwitch box */
 #define EMP_ST_KMAX 16           /* dynamic-obstacle slots per S-T scene record */
 #define EMP_ST_ROWS 40           /* s samples of the S-T lattice, speed_planning_test.py:114 */
 #define EMP_ST_COLS 16           /* t samples (0.5 s), speed_planning_test.py:116 */
@@ -216,6 +218,27 @@ int emp_st_dp_dev(const double *scenes, int kmax, int batch, const EmpStParams *
 int emp_st_dp_host(EmpPlanner *pl, const double *scenes, int kmax, int batch, const EmpStParams *p, double *out,
                    double *cost_tab, double *sdot_tab, int32_t *node_tab);
 
+/* ---- fused planning step + all-gather over NVLink peer memory --------------------------------
+ * Same as emp_sl_plan_dev, and every finished plan record is also stored into `peer_slices[r]` (r < n_peers):
+ * device pointers into the OTHER GPUs' gather buffers at this rank's slice, obtained with emp_ipc_open.
+ * The stores overlap the solves still running; a stream-ordered barrier across ranks (e.g. a 1-element NCCL
+ * all-reduce) after the call makes the gathered batch visible everywhere.  Replaces the north_star's
+ * "single NCCL all-gather of the solved paths" with P2P writes from inside the QP kernel. */
+int emp_sl_plan_p2p_dev(const double *scenes, int kmax, int batch, const EmpDpParams *dp, const EmpQpParams *qp,
+                        int n_enr_max, double *plans, int32_t *rows, int n_peers, double *const *peer_slices,
+                        void *stream);
+
+/* The corridor+QP launch of the fused step alone (for callers that time the two kernels separately). */
+int emp_sl_qp_p2p_dev(const double *scenes, int kmax, int batch, const EmpQpParams *qp, int n_enr_max,
+                      double *plans, int n_peers, double *const *peer_slices, void *stream);
+
+/* Device buffers that can be shared between the per-GPU processes of one box (CUDA IPC). */
+void *emp_device_alloc(size_t bytes);
+void emp_device_free(void *p);
+int emp_ipc_export(const void *dev_ptr, unsigned char handle[64]);
+int emp_ipc_open(const unsigned char handle[64], void **dev_ptr);
+int emp_ipc_close(void *dev_ptr);
+
 /* FP64 FMA micro-benchmark (roofline denominator; absent from MEASURED_PEAKS.json).
  * Returns achieved TFLOP/s through *tflops. */
 int emp_fp64_peak(int iters, double *tflops, double *ms);
@@ -237,6 +260,10 @@ int emp_qp_host(EmpPlanner *pl, const double *l_min, const double *l_max, const 
                 int n, int batch, const EmpQpParams *p, double *out_l_dl_ddl, int32_t *status_iters);
 int emp_corridor_host(EmpPlanner *pl, const double *dp_s, const double *dp_l, int n, const double *scenes,
                       int batch, const EmpQpParams *p, double *lmin_lmax, int32_t *status_iters);
+/* Page-locked host buffers.  The *_host entry points DMA straight from/to buffers that are page-locked
+ * (these, cudaHostRegister'ed, or torch pinned memory) and stage pageable ones through internal pinned buffers. */
+void *emp_host_alloc(size_t bytes);
+void emp_host_free(void *p);
 /* Kernel-only time (ms, CUDA events on the planner's stream) of the last *_host call. */
 double emp_planner_last_kernel_ms(const EmpPlanner *pl);
 
