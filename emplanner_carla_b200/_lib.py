@@ -80,6 +80,10 @@ _SIGNATURES = {
     "emp_ipc_export": (C.c_int, [_P, _P]),
     "emp_ipc_open": (C.c_int, [_P, C.POINTER(_P)]),
     "emp_ipc_close": (C.c_int, [_P]),
+    "emp_quintic_host": (C.c_int, [_P, _P, C.c_int, _P]),
+    "emp_edge_cost_host": (C.c_int, [_P, _P, C.c_int, _P, _P, C.c_int, _DPP, _P]),
+    "emp_obs_cost_host": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double, _P]),
+    "emp_enrich_host": (C.c_int, [_P, _P, _P, _P, C.c_int, C.c_int, C.c_double, C.c_int, _P, _P, _P]),
     "emp_host_alloc": (_P, [C.c_size_t]),
     "emp_host_free": (None, [_P]),
     "emp_planner_last_kernel_ms": (C.c_double, [_P]),

@@ -270,6 +270,44 @@ class HostPlanner:
                                                       _ptr(cart), _ptr(ncart)))
         return cart, ncart
 
+    # ---- stand-alone pieces of the S-L DP (K6) -------------------------------------------------
+    def quintic(self, conds):
+        """cal_quintic_coefficient for rows (start_l, start_dl, start_ddl, end_l, end_dl, end_ddl, start_s, end_s)."""
+        conds = np.ascontiguousarray(conds, dtype=np.float64).reshape(-1, 8)
+        out = np.zeros((conds.shape[0], 6))
+        _lib.check(_lib.lib().emp_quintic_host(self._h, _ptr(conds), conds.shape[0], _ptr(out)))
+        return out
+
+    def edge_cost(self, edges, obs_s, obs_l, dp):
+        """cal_start_cost / cal_neighbor_cost for rows (start_s, start_l, start_dl, start_ddl, end_s, end_l)."""
+        edges = np.ascontiguousarray(edges, dtype=np.float64).reshape(-1, 6)
+        obs_s = np.ascontiguousarray(obs_s, dtype=np.float64).reshape(-1)
+        obs_l = np.ascontiguousarray(obs_l, dtype=np.float64).reshape(-1)
+        out = np.zeros(edges.shape[0])
+        k = obs_s.shape[0]
+        _lib.check(_lib.lib().emp_edge_cost_host(self._h, _ptr(edges), edges.shape[0], _ptr(obs_s) if k else None,
+                                                 _ptr(obs_l) if k else None, k, C.byref(dp), _ptr(out)))
+        return out
+
+    def obs_cost(self, square_d, w_collision, danger_dis=4, safe_dis=6):
+        square_d = np.ascontiguousarray(square_d, dtype=np.float64)
+        square_d = square_d.reshape(1, -1) if square_d.ndim == 1 else square_d.reshape(square_d.shape[0], -1)
+        out = np.zeros(square_d.shape[0])
+        _lib.check(_lib.lib().emp_obs_cost_host(self._h, _ptr(square_d), square_d.shape[1], square_d.shape[0],
+                                                float(w_collision), float(danger_dis), float(safe_dis), _ptr(out)))
+        return out
+
+    def enrich(self, node_s, node_l, start, resolution, n_max):
+        node_s = np.ascontiguousarray(node_s, dtype=np.float64)
+        node_l = np.ascontiguousarray(node_l, dtype=np.float64)
+        start = np.ascontiguousarray(start, dtype=np.float64).reshape(-1, 4)
+        B, Cn = node_s.shape
+        os_, ol_ = np.zeros((B, n_max)), np.zeros((B, n_max))
+        n_out = np.zeros(B, dtype=np.int32)
+        _lib.check(_lib.lib().emp_enrich_host(self._h, _ptr(node_s), _ptr(node_l), _ptr(start), Cn, B, float(resolution),
+                                              int(n_max), _ptr(os_), _ptr(ol_), _ptr(n_out)))
+        return os_, ol_, n_out
+
     # ---- reference-line smoother (K5) ----------------------------------------------------------
     def smooth_lines(self, xy, sp, npts=None):
         """smooth_reference_line (+ cal_heading_kappa) for a batch of polylines xy [B, M, 2].

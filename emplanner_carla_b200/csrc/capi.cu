@@ -10,6 +10,7 @@
 #include "frenet_kernels.h"
 #include "st_kernels.h"
 #include "smooth_kernels.h"
+#include "misc_kernels.h"
 
 namespace {
 
@@ -619,6 +620,85 @@ int emp_st_dp_host(EmpPlanner *pl, const double *scenes, int kmax, int batch, co
     EMP_CK(cudaStreamSynchronize(pl->stream), "planner stream");
     cudaEventElapsedTime(&pl->last_ms, pl->ev0, pl->ev1);
     return rc;
+}
+
+int emp_quintic_host(EmpPlanner *pl, const double *in, int n, double *out) {
+    if (!pl || !in || !out) return fail(-1, "NULL argument");
+    if (n <= 0) return n == 0 ? 0 : fail(-2, "bad n");
+    EMP_CK(cudaSetDevice(pl->device), "cudaSetDevice");
+    {
+        Tmp t(pl->stream);
+        const double *d_in = t.in(in, (size_t)n * 8);
+        double *d_out = t.out<double>((size_t)n * 6);
+        if (t.err != cudaSuccess) return fail_cuda(t.err, "quintic staging");
+        EMP_CK(emp::launch_quintic(d_in, d_out, n, pl->stream), "quintic launch");
+        t.back(out, d_out, (size_t)n * 6);
+        if (t.err != cudaSuccess) return fail_cuda(t.err, "quintic copy-back");
+    }
+    EMP_CK(cudaStreamSynchronize(pl->stream), "planner stream");
+    return 0;
+}
+
+int emp_edge_cost_host(EmpPlanner *pl, const double *edges, int n_edges, const double *obs_s, const double *obs_l,
+                       int n_obs, const EmpDpParams *p, double *out) {
+    if (!pl || !edges || !out || !p) return fail(-1, "NULL argument");
+    if (n_edges <= 0) return n_edges == 0 ? 0 : fail(-2, "bad n_edges");
+    if (n_obs < 0 || (n_obs > 0 && (!obs_s || !obs_l))) return fail(-2, "bad obstacle list");
+    EMP_CK(cudaSetDevice(pl->device), "cudaSetDevice");
+    {
+        Tmp t(pl->stream);
+        const double *d_e = t.in(edges, (size_t)n_edges * 6);
+        const double *d_os = t.in(obs_s, (size_t)n_obs), *d_ol = t.in(obs_l, (size_t)n_obs);
+        double *d_out = t.out<double>((size_t)n_edges);
+        if (t.err != cudaSuccess) return fail_cuda(t.err, "edge_cost staging");
+        emp::EdgeParams P{p->sample_s, p->w_collision, p->w_smooth[0], p->w_smooth[1], p->w_smooth[2], p->w_ref};
+        EMP_CK(emp::launch_edge_cost(d_e, d_os, d_ol, n_obs, n_edges, P, d_out, pl->stream), "edge_cost launch");
+        t.back(out, d_out, (size_t)n_edges);
+        if (t.err != cudaSuccess) return fail_cuda(t.err, "edge_cost copy-back");
+    }
+    EMP_CK(cudaStreamSynchronize(pl->stream), "planner stream");
+    return 0;
+}
+
+int emp_obs_cost_host(EmpPlanner *pl, const double *square_d, int n, int batch, double w_collision, double danger_dis,
+                      double safe_dis, double *out) {
+    if (!pl || !square_d || !out) return fail(-1, "NULL argument");
+    if (batch <= 0 || n < 0) return batch == 0 ? 0 : fail(-2, "bad sizes");
+    EMP_CK(cudaSetDevice(pl->device), "cudaSetDevice");
+    {
+        Tmp t(pl->stream);
+        const double *d_in = t.in(square_d, (size_t)batch * (n > 0 ? n : 1));
+        double *d_out = t.out<double>((size_t)batch);
+        if (t.err != cudaSuccess) return fail_cuda(t.err, "obs_cost staging");
+        EMP_CK(emp::launch_obs_cost(d_in, n, batch, w_collision, danger_dis * danger_dis, safe_dis * safe_dis, d_out,
+                                    pl->stream), "obs_cost launch");
+        t.back(out, d_out, (size_t)batch);
+        if (t.err != cudaSuccess) return fail_cuda(t.err, "obs_cost copy-back");
+    }
+    EMP_CK(cudaStreamSynchronize(pl->stream), "planner stream");
+    return 0;
+}
+
+int emp_enrich_host(EmpPlanner *pl, const double *node_s, const double *node_l, const double *start, int C, int batch,
+                    double resolution, int n_max, double *out_s, double *out_l, int32_t *n_out) {
+    if (!pl || !node_s || !node_l || !start || !out_s || !out_l || !n_out) return fail(-1, "NULL argument");
+    if (batch <= 0 || C < 1 || n_max < 1 || !(resolution > 0)) return batch == 0 ? 0 : fail(-2, "bad sizes");
+    EMP_CK(cudaSetDevice(pl->device), "cudaSetDevice");
+    {
+        Tmp t(pl->stream);
+        const double *d_s = t.in(node_s, (size_t)batch * C), *d_l = t.in(node_l, (size_t)batch * C);
+        const double *d_st = t.in(start, (size_t)batch * 4);
+        double *d_os = t.out<double>((size_t)batch * n_max), *d_ol = t.out<double>((size_t)batch * n_max);
+        int32_t *d_n = t.out<int32_t>((size_t)batch);
+        if (t.err != cudaSuccess) return fail_cuda(t.err, "enrich staging");
+        EMP_CK(emp::launch_enrich(d_s, d_l, d_st, C, batch, resolution, n_max, d_os, d_ol, d_n, pl->stream), "enrich launch");
+        t.back(out_s, d_os, (size_t)batch * n_max);
+        t.back(out_l, d_ol, (size_t)batch * n_max);
+        t.back(n_out, d_n, (size_t)batch);
+        if (t.err != cudaSuccess) return fail_cuda(t.err, "enrich copy-back");
+    }
+    EMP_CK(cudaStreamSynchronize(pl->stream), "planner stream");
+    return 0;
 }
 
 void *emp_host_alloc(size_t bytes) {

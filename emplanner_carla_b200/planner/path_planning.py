@@ -113,3 +113,43 @@ def frenet_2_x_y_theta_kappa(plan_start_s, plan_start_l, enriched_s_list: list, 
     from . import planning_utils
     return planning_utils.smooth_reference_line(target_xy)
 
+
+
+def enrich_DP_s_l(DP_s_list, DP_l_list, plan_start_s, plan_start_l, plan_start_dl, plan_start_ddl, resolution=1):
+    """Densify the DP nodes along their quintic connections (reference :378-432)."""
+    s = np.asarray(DP_s_list, dtype=np.float64)[None]
+    l = np.asarray(DP_l_list, dtype=np.float64)[None]
+    span = max(float(s[0, -1] - plan_start_s), 0.0)
+    n_max = int(span / float(resolution)) + s.shape[1] + 2
+    os_, ol_, n = _runtime.planner().enrich(s, l, [[plan_start_s, plan_start_l, plan_start_dl, plan_start_ddl]],
+                                            resolution, n_max)
+    return list(os_[0, :n[0]]), list(ol_[0, :n[0]])
+
+
+def cal_start_cost(obs_s_list, obs_l_list, begin_s, begin_l, begin_dl, begin_ddl, cur_node_row, row,
+                   sample_s, sample_l, w_cost_collision, w_cost_smooth, w_cost_ref):
+    """Cost of the edge plan start -> lattice node (row cur_node_row, first column) (reference :435-514).
+    Returns a (1, 1) ndarray like the reference."""
+    end_l = ((row + 1) / 2 - 1 - cur_node_row) * sample_l
+    dp = api.dp_params(w_collision_cost=w_cost_collision, w_smooth_cost=w_cost_smooth, w_reference_cost=w_cost_ref,
+                       sample_s=sample_s, sample_l=sample_l)
+    c = _runtime.planner().edge_cost([[begin_s, begin_l, begin_dl, begin_ddl, begin_s + sample_s, end_l]],
+                                     obs_s_list, obs_l_list, dp)
+    return np.array([[c[0]]])
+
+
+def cal_neighbor_cost(obs_s_list, obs_l_list, pre_node_s, pre_node_l, cur_node_s, cur_node_l, sample_s,
+                      w_cost_collision, w_cost_smooth, w_cost_ref):
+    """Cost of the edge between two lattice nodes of adjacent columns (reference :517-585).
+    Returns a (1, 1) ndarray like the reference."""
+    dp = api.dp_params(w_collision_cost=w_cost_collision, w_smooth_cost=w_cost_smooth, w_reference_cost=w_cost_ref,
+                       sample_s=sample_s)
+    c = _runtime.planner().edge_cost([[pre_node_s, pre_node_l, 0.0, 0.0, cur_node_s, cur_node_l]],
+                                     obs_s_list, obs_l_list, dp)
+    return np.array([[c[0]]])
+
+
+def cal_obs_cost(w_cost_collision, square_d: np.ndarray, danger_dis=4, safe_dis=6):
+    """Obstacle cost of one edge from the squared distances of its samples (reference :588-609)."""
+    return float(_runtime.planner().obs_cost(np.asarray(square_d, dtype=np.float64).reshape(1, -1), w_cost_collision,
+                                             danger_dis, safe_dis)[0])

@@ -112,3 +112,28 @@ def cal_heading_kappa(frenet_path_xy_list: list):
     sp = api.smooth_params(heading_only=True)
     out, _, _ = _runtime.planner().smooth_lines(_pts(frenet_path_xy_list), sp)
     return list(out[0, :, 2]), list(out[0, :, 3])
+
+
+def cal_quintic_coefficient(start_l, start_dl, start_ddl, end_l, end_dl, end_ddl, start_s, end_s):
+    """Quintic l(s) through the two boundary states; coefficients of the absolute-s power basis
+    [a0..a5] (reference :671-703).  Closed form on the GPU instead of the reference's 6x6 matrix inverse: the
+    two agree to the inverse's own rounding noise (its condition number reaches 1e16 at s ~ 75 m)."""
+    c = _runtime.planner().quintic([[start_l, start_dl, start_ddl, end_l, end_dl, end_ddl, start_s, end_s]])
+    return list(c[0])
+
+
+def cal_projection_s_fun(local_path_opt: list, match_index_list: list, xy_list: list, s_map: list):
+    """s of the projections of points whose match indices are given (reference :429-445)."""
+    if len(match_index_list) == 0:
+        return []
+    line = _line(local_path_opt)
+    out = []
+    # one GPU call per distinct match index keeps the kernel's "scan from the given node" semantics trivial:
+    # a 1-node window makes the nearest-node scan return exactly that node
+    for mi, pt in zip(match_index_list, xy_list):
+        mi = int(mi)
+        win = np.repeat(line[:, mi:mi + 1, :], 2, axis=1)            # the kernel needs >= 2 nodes
+        smap = np.array([[s_map[mi], s_map[mi]]], dtype=np.float64)
+        r = _runtime.planner().frenet_project(win, points=_pts([pt]), s_map_in=smap, want=("sl",))
+        out.append(r["sl"][0, 0, 0])
+    return out

@@ -218,6 +218,23 @@ int emp_st_dp_dev(const double *scenes, int kmax, int batch, const EmpStParams *
 int emp_st_dp_host(EmpPlanner *pl, const double *scenes, int kmax, int batch, const EmpStParams *p, double *out,
                    double *cost_tab, double *sdot_tab, int32_t *node_tab);
 
+/* ---- stand-alone pieces of the S-L DP (K6), host-buffer entry points ------------------------------
+ * emp_quintic_host:   planning_utils.cal_quintic_coefficient (:671-703).  in [n,8] = (start_l, start_dl, start_ddl,
+ *                     end_l, end_dl, end_ddl, start_s, end_s); out [n,6] coefficients of the absolute-s power basis.
+ * emp_edge_cost_host: path_planning.cal_start_cost (:435) / cal_neighbor_cost (:517).  edges [n,6] = (start_s,
+ *                     start_l, start_dl, start_ddl, end_s, end_l); obstacles shared by all edges; uses p->sample_s
+ *                     (sample spacing sample_s/10), p->w_collision, p->w_smooth, p->w_ref.  out [n].
+ * emp_obs_cost_host:  path_planning.cal_obs_cost (:588).  square_d [batch,n] -> out [batch].
+ * emp_enrich_host:    path_planning.enrich_DP_s_l (:378).  node_s/node_l [batch,C], start [batch,4] = (s,l,dl,ddl);
+ *                     out_s/out_l [batch,n_max], n_out [batch]. */
+int emp_quintic_host(EmpPlanner *pl, const double *in, int n, double *out);
+int emp_edge_cost_host(EmpPlanner *pl, const double *edges, int n_edges, const double *obs_s, const double *obs_l,
+                       int n_obs, const EmpDpParams *p, double *out);
+int emp_obs_cost_host(EmpPlanner *pl, const double *square_d, int n, int batch, double w_collision, double danger_dis,
+                      double safe_dis, double *out);
+int emp_enrich_host(EmpPlanner *pl, const double *node_s, const double *node_l, const double *start, int C, int batch,
+                    double resolution, int n_max, double *out_s, double *out_l, int32_t *n_out);
+
 /* ---- fused planning step + all-gather over NVLink peer memory --------------------------------
  * Same as emp_sl_plan_dev, and every finished plan record is also stored into `peer_slices[r]` (r < n_peers):
  * device pointers into the OTHER GPUs' gather buffers at this rank's slice, obtained with emp_ipc_open.

@@ -127,6 +127,75 @@ def _edge_cost_inv(obs_s, obs_l, s0, l0, dl0, ddl0, s1, l1, T, w_col, w_s, w_ref
     return float((smooth + coll + ref).squeeze())
 
 
+def quintic_closed(l0, dl0, ddl0, l1, dl1, ddl1, s0, s1):
+    """cal_quintic_coefficient (planning_utils.py:671-703) in closed form: local coefficients in u = s - s0,
+    expanded to the absolute-s power basis the reference returns."""
+    T = s1 - s0
+    iT = 1.0 / T
+    iT3 = (iT * iT) * iT
+    iT4 = iT3 * iT
+    iT5 = iT4 * iT
+    D = l1 - l0
+    T2 = T * T
+    a = [l0, dl0, ddl0 / 2.0,
+         ((20.0 * D - (8.0 * dl1 + 12.0 * dl0) * T) - (3.0 * ddl0 - ddl1) * T2) * (0.5 * iT3),
+         ((-30.0 * D + (14.0 * dl1 + 16.0 * dl0) * T) + (3.0 * ddl0 - 2.0 * ddl1) * T2) * (0.5 * iT4),
+         ((12.0 * D - (6.0 * (dl1 + dl0)) * T) - (ddl0 - ddl1) * T2) * (0.5 * iT5)]
+    m = -s0
+    m2, m3, m4, m5 = m * m, m * m * m, (m * m * m) * m, ((m * m * m) * m) * m
+    return [a[0] + a[1] * m + a[2] * m2 + a[3] * m3 + a[4] * m4 + a[5] * m5,
+            a[1] + 2.0 * a[2] * m + 3.0 * a[3] * m2 + 4.0 * a[4] * m3 + 5.0 * a[5] * m4,
+            a[2] + 3.0 * a[3] * m + 6.0 * a[4] * m2 + 10.0 * a[5] * m3,
+            a[3] + 4.0 * a[4] * m + 10.0 * a[5] * m2,
+            a[4] + 5.0 * a[5] * m,
+            a[5]]
+
+
+def edge_cost_closed(obs_s, obs_l, s0, l0, dl0, ddl0, s1, l1, sample_s, w_col, w_s, w_ref):
+    """One edge in closed form (what csrc/misc.cu::edge_cost_kernel and column 0 of K1 compute):
+    cal_start_cost / cal_neighbor_cost (path_planning.py:435-585) with the quintic evaluated in u = s - s0."""
+    T = s1 - s0
+    iT = 1.0 / T
+    iT3 = (iT * iT) * iT
+    iT4 = iT3 * iT
+    iT5 = iT4 * iT
+    D = l1 - l0
+    T2 = T * T
+    a1, a2 = dl0, ddl0 / 2.0
+    a3 = ((20.0 * D - (8.0 * 0.0 + 12.0 * dl0) * T) - (3.0 * ddl0 - 0.0) * T2) * (0.5 * iT3)
+    a4 = ((-30.0 * D + (14.0 * 0.0 + 16.0 * dl0) * T) + (3.0 * ddl0 - 2.0 * 0.0) * T2) * (0.5 * iT4)
+    a5 = ((12.0 * D - (6.0 * (0.0 + dl0)) * T) - (ddl0 - 0.0) * T2) * (0.5 * iT5)
+    c4 = a4 - (5.0 * a5) * s0
+    c3 = (a3 - (4.0 * a4) * s0) + (10.0 * a5) * (s0 * s0)
+    alpha, beta = 6.0 * c3, 24.0 * c4 + 120.0 * a5
+    sdl = sddl = sj = sl2 = 0.0
+    sm, lm = [], []
+    for m in range(NSAMP):
+        u = (m * sample_s) / 10.0
+        s = s0 + u
+        l = l0 + u * (a1 + u * (a2 + u * (a3 + u * (a4 + u * a5))))
+        dl = a1 + u * (2.0 * a2 + u * (3.0 * a3 + u * (4.0 * a4 + u * (5.0 * a5))))
+        ddl = 2.0 * a2 + u * (6.0 * a3 + u * (12.0 * a4 + u * (20.0 * a5)))
+        jm = alpha + beta * s
+        sdl, sddl, sj, sl2 = sdl + dl * dl, sddl + ddl * ddl, sj + jm * jm, sl2 + l * l
+        sm.append(s)
+        lm.append(l)
+    smooth = (w_s[0] * sdl + w_s[1] * sddl) + w_s[2] * sj
+    coll = 0.0
+    for o in range(len(obs_s)):
+        one = 0.0
+        for m in range(NSAMP):
+            dlon, dlat = obs_s[o] - sm[m], obs_l[o] - lm[m]
+            d2 = dlon * dlon + dlat * dlat
+            if d2 <= DANGER2:
+                one = one + w_col
+                break
+            elif d2 < SAFE2:
+                one = one + NEAR_COST / d2
+        coll = coll + one
+    return (smooth + coll) + w_ref * sl2
+
+
 def dp_batch(obs_s, obs_l, nobs, s0, l0, dl0, ddl0, sampling_res=2, w_col=1e12,
              w_smooth=(300, 1000, 5000), w_ref=20, row=12, col=6, sample_s=15,
              sample_l=1.5, mode="closed", return_tables=False):

@@ -86,3 +86,55 @@ def test_more_than_eight_obstacles_and_empty_list(planner_pkg):
     assert np.array_equal(s, so) and np.abs(np.array(l) - lo).max() < 1e-12
     s, l = pp.DP_algorithm([], [], 0.7, -0.1, 0.0, 0.0)        # no obstacle: straight branch (:362-363)
     assert all(v == 0.0 for v in l[8:])
+
+
+def test_standalone_dp_pieces(planner_pkg):
+    """cal_start_cost / cal_neighbor_cost / cal_obs_cost / enrich_DP_s_l / cal_quintic_coefficient by their
+    reference names: bit-exact against the closed-form oracle, and within the reference's own inversion noise
+    of the reference-faithful ('inv') oracle."""
+    import sys
+    from oracle import sl_dp
+    pp = planner_pkg
+    from planner import planning_utils as pu
+    obs_s, obs_l = [20.0, 33.0, 47.5], [0.5, -1.0, 2.0]
+    w = (1e12, [300, 1000, 5000], 20)
+    # neighbour edges at several stations, incl. collisions and the near zone
+    for (s0, lk, li) in [(15.3, 0.75, -0.75), (30.3, -2.25, 2.25), (45.3, 0.75, 0.75), (0.3, -8.25, 8.25)]:
+        got = pp.cal_neighbor_cost(obs_s, obs_l, s0, lk, s0 + 15, li, 15, *w)
+        assert got.shape == (1, 1)
+        exact = sl_dp.edge_cost_closed(obs_s, obs_l, s0, lk, 0.0, 0.0, s0 + 15, li, 15, w[0], w[1], w[2])
+        faithful = sl_dp._edge_cost_inv(obs_s, obs_l, s0, lk, 0, 0, s0 + 15, li, 15, w[0], w[1], w[2])
+        assert got[0, 0] == exact
+        assert abs(got[0, 0] - faithful) <= 1e-9 * abs(faithful)
+    got = pp.cal_start_cost(obs_s, obs_l, 0.4, 0.2, 0.01, -0.003, 3, 12, 15, 1.5, *w)
+    end_l = ((12 + 1) / 2 - 1 - 3) * 1.5
+    assert got[0, 0] == sl_dp.edge_cost_closed(obs_s, obs_l, 0.4, 0.2, 0.01, -0.003, 15.4, end_l, 15, w[0], w[1], w[2])
+    assert abs(got[0, 0] - sl_dp._edge_cost_inv(obs_s, obs_l, 0.4, 0.2, 0.01, -0.003, 15.4, end_l, 15, *w)) <= 1e-9 * got[0, 0]
+    # cal_obs_cost: Q8 order dependence
+    d2 = np.array([[40.0], [30.0], [20.0], [9.0], [20.0], [50.0], [50.0], [50.0], [50.0], [50.0]])
+    assert pp.cal_obs_cost(1e12, d2) == 5000 / 30.0 + 5000 / 20.0 + 1e12
+    assert pp.cal_obs_cost(7.0, np.full((10, 1), 36.0)) == 0.0
+    # enrich_DP_s_l with non-uniform nodes and resolution 1
+    S, L = [14.2, 30.0, 44.9, 61.0], [0.75, -0.75, -0.75, 2.25]
+    es, el = pp.enrich_DP_s_l(S, L, 0.2, 0.1, 0.02, -0.001, resolution=1)
+    os_, ol_ = sl_dp.enrich(S, L, 0.2, 0.1, 0.02, -0.001, resolution=1)
+    assert len(es) == len(os_) and np.array_equal(es, os_) and np.abs(np.array(el) - ol_).max() < 1e-12
+    # cal_quintic_coefficient: boundary conditions reproduced, agrees with the reference's inverse within its noise
+    c = pu.cal_quintic_coefficient(0.3, 0.02, -0.004, -1.5, 0.01, 0.002, 12.5, 27.5)
+    ref = sl_dp._quintic_inv(0.3, 0.02, -0.004, -1.5, 0.01, 0.002, 12.5, 27.5)
+    p = np.polynomial.polynomial
+    for s, want in ((12.5, (0.3, 0.02, -0.004)), (27.5, (-1.5, 0.01, 0.002))):
+        for k in range(3):
+            assert abs(p.polyval(s, p.polyder(c, k)) - want[k]) < 1e-9
+    assert np.allclose(c, ref, rtol=1e-6, atol=1e-9)
+    assert c == sl_dp.quintic_closed(0.3, 0.02, -0.004, -1.5, 0.01, 0.002, 12.5, 27.5)
+    # cal_projection_s_fun with explicit match indices
+    g = load_golden("frenet.npz")
+    from oracle import frenet as ofr
+    line = [tuple(r) for r in g["line"][0]]
+    smap = list(g["smap"][0])
+    pts = [tuple(p) for p in g["obs_xy"][0]]
+    mi, _ = ofr.match_projection(pts, line)
+    want = ofr.projection_s(line, mi, pts, smap)
+    got = pu.cal_projection_s_fun(line, mi, pts, smap)
+    assert np.abs(np.array(got) - np.array(want)).max() < 1e-9
