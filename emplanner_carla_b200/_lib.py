@@ -40,6 +40,15 @@ class SmoothParams(C.Structure):
                 ("maxiters", C.c_int32), ("heading_only", C.c_int32)]
 
 
+class MiscAux(C.Structure):
+    """EmpMiscAux: side inputs of emp_misc_host."""
+    _fields_ = [("obs4", C.c_void_p), ("n_obs", C.c_int32), ("n_nodes", C.c_int32), ("sdot_tab", C.c_void_p),
+                ("path", C.c_void_p), ("s_map", C.c_void_p), ("v0", C.c_double), ("st", StParams)]
+
+
+OP_ST_GRAPH, OP_START_CONDITION, OP_DY_OBS_DERI, OP_INDEX2S = 0, 1, 2, 3
+OP_ST_DP_COST, OP_ST_OBS_COST, OP_ST_COLLISION, OP_FRENET2CART, OP_CALC_PROJ_POINT = 4, 5, 6, 7, 8
+
 _P = C.c_void_p
 _DPP = C.POINTER(DpParams)
 _QPP = C.POINTER(QpParams)
@@ -84,6 +93,7 @@ _SIGNATURES = {
     "emp_edge_cost_host": (C.c_int, [_P, _P, C.c_int, _P, _P, C.c_int, _DPP, _P]),
     "emp_obs_cost_host": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double, _P]),
     "emp_enrich_host": (C.c_int, [_P, _P, _P, _P, C.c_int, C.c_int, C.c_double, C.c_int, _P, _P, _P]),
+    "emp_misc_host": (C.c_int, [_P, C.c_int, _P, C.c_int, C.c_int, C.POINTER(MiscAux), _P]),
     "emp_host_alloc": (_P, [C.c_size_t]),
     "emp_host_free": (None, [_P]),
     "emp_planner_last_kernel_ms": (C.c_double, [_P]),

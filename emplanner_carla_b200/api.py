@@ -308,6 +308,30 @@ class HostPlanner:
                                               int(n_max), _ptr(os_), _ptr(ol_), _ptr(n_out)))
         return os_, ol_, n_out
 
+    # ---- small S-T / speed-draft helpers (K7) ---------------------------------------------------
+    def misc(self, op, inp, n, batch, out_shape, obs4=None, sdot_tab=None, v0=0.0, st=None, path=None, s_map=None):
+        """emp_misc_host: see include/emplanner.h for the per-op layouts."""
+        inp = np.ascontiguousarray(inp, dtype=np.float64)
+        out = np.zeros(out_shape)
+        aux = _lib.MiscAux()
+        keep = []
+        def ptr(arr):
+            if arr is None:
+                return None
+            arr = np.ascontiguousarray(arr, dtype=np.float64)
+            keep.append(arr)
+            return arr.ctypes.data
+        aux.obs4 = ptr(obs4)
+        aux.n_obs = 0 if obs4 is None else int(np.asarray(obs4).shape[-1])
+        aux.sdot_tab = ptr(sdot_tab)
+        aux.path = ptr(path)
+        aux.s_map = ptr(s_map)
+        aux.n_nodes = 0 if s_map is None else int(np.asarray(s_map).shape[-1])
+        aux.v0 = float(v0)
+        aux.st = st if st is not None else _lib.st_params()
+        _lib.check(_lib.lib().emp_misc_host(self._h, int(op), _ptr(inp), int(n), int(batch), C.byref(aux), _ptr(out)))
+        return out
+
     # ---- reference-line smoother (K5) ----------------------------------------------------------
     def smooth_lines(self, xy, sp, npts=None):
         """smooth_reference_line (+ cal_heading_kappa) for a batch of polylines xy [B, M, 2].

@@ -15,7 +15,7 @@ LIB = os.path.join(PKG, "libemplanner.so")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-Xcompiler", "-ffp-contract=off",
           "--expt-relaxed-constexpr"]
-UNITS = [("sl_dp.cu", ["-fmad=false"]), ("sl_qp.cu", []), ("st_dp.cu", ["-fmad=false"]), ("frenet.cu", ["-fmad=false"]), ("smooth_qp.cu", []), ("misc.cu", ["-fmad=false"]),
+UNITS = [("sl_dp.cu", ["-fmad=false"]), ("sl_qp.cu", []), ("st_dp.cu", ["-fmad=false"]), ("frenet.cu", ["-fmad=false"]), ("smooth_qp.cu", []), ("misc.cu", ["-fmad=false"]), ("st_misc.cu", ["-fmad=false"]),
          ("fp64_peak.cu", []), ("capi.cu", [])]
 
 

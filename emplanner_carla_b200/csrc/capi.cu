@@ -11,6 +11,7 @@
 #include "st_kernels.h"
 #include "smooth_kernels.h"
 #include "misc_kernels.h"
+#include "st_misc_kernels.h"
 
 namespace {
 
@@ -696,6 +697,64 @@ int emp_enrich_host(EmpPlanner *pl, const double *node_s, const double *node_l, 
         t.back(out_l, d_ol, (size_t)batch * n_max);
         t.back(n_out, d_n, (size_t)batch);
         if (t.err != cudaSuccess) return fail_cuda(t.err, "enrich copy-back");
+    }
+    EMP_CK(cudaStreamSynchronize(pl->stream), "planner stream");
+    return 0;
+}
+
+int emp_misc_host(EmpPlanner *pl, int op, const double *in, int n, int batch, const EmpMiscAux *aux, double *out) {
+    if (!pl || !in || !out) return fail(-1, "NULL argument");
+    if (n < 0 || batch < 0) return fail(-2, "bad sizes");
+    EMP_CK(cudaSetDevice(pl->device), "cudaSetDevice");
+    size_t n_in = 0, n_out = 0;
+    switch (op) {
+        case EMP_OP_ST_GRAPH: n_in = (size_t)batch * 4 * n; n_out = n_in; break;
+        case EMP_OP_START_CONDITION: n_in = (size_t)batch * 5; n_out = (size_t)batch * 2; break;
+        case EMP_OP_DY_OBS_DERI: n_in = (size_t)batch * 5 * n; n_out = (size_t)batch * 3 * 128; break;
+        case EMP_OP_INDEX2S: n_in = (size_t)batch * 2 * n; n_out = (size_t)batch * n; break;
+        case EMP_OP_ST_DP_COST: case EMP_OP_ST_OBS_COST: n_in = (size_t)n * 4; n_out = n; break;
+        case EMP_OP_ST_COLLISION: n_in = n; n_out = n; break;
+        case EMP_OP_FRENET2CART: case EMP_OP_CALC_PROJ_POINT: n_in = (size_t)n * 4; n_out = (size_t)n * 4; break;
+        default: return fail(-2, "unknown op");
+    }
+    if (n_in == 0 || n_out == 0) return 0;
+    const bool cost_op = op == EMP_OP_ST_DP_COST || op == EMP_OP_ST_OBS_COST || op == EMP_OP_ST_COLLISION;
+    const bool cart_op = op == EMP_OP_FRENET2CART || op == EMP_OP_CALC_PROJ_POINT;
+    if ((cost_op || cart_op) && !aux) return fail(-1, "aux is NULL");
+    if (cost_op && (aux->n_obs < 0 || aux->n_obs > EMP_ST_KMAX)) return fail(-2, "n_obs must be in [0, 16]");
+    if (cart_op && (!aux->path || !aux->s_map || aux->n_nodes < 2)) return fail(-2, "bad path / s_map");
+    {
+        Tmp t(pl->stream);
+        const double *d_in = t.in(in, n_in);
+        double *d_out = t.out<double>(n_out);
+        const double *d_obs = nullptr, *d_tab = nullptr, *d_path = nullptr, *d_smap = nullptr;
+        if (cost_op) {
+            d_obs = t.in(aux->obs4, (size_t)4 * aux->n_obs);
+            d_tab = t.in(aux->sdot_tab, (size_t)EMP_ST_ROWS * EMP_ST_COLS);
+        }
+        if (cart_op) {
+            d_path = t.in(aux->path, (size_t)4 * aux->n_nodes);
+            d_smap = t.in(aux->s_map, (size_t)aux->n_nodes);
+        }
+        if (t.err != cudaSuccess) return fail_cuda(t.err, "misc staging");
+        cudaError_t e = cudaSuccess;
+        switch (op) {
+            case EMP_OP_ST_GRAPH: e = emp::launch_st_graph(d_in, n, batch, d_out, pl->stream); break;
+            case EMP_OP_START_CONDITION: e = emp::launch_start_condition(d_in, batch, d_out, pl->stream); break;
+            case EMP_OP_DY_OBS_DERI: e = emp::launch_dy_obs_deri(d_in, n, batch, d_out, pl->stream); break;
+            case EMP_OP_INDEX2S: e = emp::launch_index2s(d_in, n, batch, d_out, pl->stream); break;
+            case EMP_OP_ST_DP_COST: case EMP_OP_ST_OBS_COST: case EMP_OP_ST_COLLISION:
+                if (op == EMP_OP_ST_DP_COST && !d_tab) return fail(-1, "sdot_tab is NULL");
+                e = emp::launch_st_cost(op == EMP_OP_ST_DP_COST ? 0 : (op == EMP_OP_ST_OBS_COST ? 1 : 2), d_in, n, d_obs,
+                                        aux->n_obs, d_tab, aux->v0, aux->st, d_out, pl->stream);
+                break;
+            default:
+                e = emp::launch_frenet2cart(d_in, n, d_path, d_smap, aux->n_nodes, op == EMP_OP_CALC_PROJ_POINT, d_out,
+                                            pl->stream);
+        }
+        if (e != cudaSuccess) return fail_cuda(e, "misc launch");
+        t.back(out, d_out, n_out);
+        if (t.err != cudaSuccess) return fail_cuda(t.err, "misc copy-back");
     }
     EMP_CK(cudaStreamSynchronize(pl->stream), "planner stream");
     return 0;

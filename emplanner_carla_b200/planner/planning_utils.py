@@ -7,7 +7,7 @@ Reference line numbers cite planning_utils.py @ 1f115a5.  Not provided: the thre
 """
 import numpy as np
 
-from emplanner_carla_b200 import api
+from emplanner_carla_b200 import api, _lib
 from . import _runtime
 
 
@@ -137,3 +137,43 @@ def cal_projection_s_fun(local_path_opt: list, match_index_list: list, xy_list: 
         r = _runtime.planner().frenet_project(win, points=_pts([pt]), s_map_in=smap, want=("sl",))
         out.append(r["sl"][0, 0, 0])
     return out
+
+
+def trajectory_index2s(trajectory_x, trajectory_y):
+    """Cumulative arc length of a NaN-padded trajectory (reference :758-780)."""
+    xy = np.array([trajectory_x, trajectory_y], dtype=np.float64)
+    n = xy.shape[1]
+    return _runtime.planner().misc(_lib.OP_INDEX2S, xy[None], n, 1, (1, n))[0]
+
+
+def cal_dy_obs_deri(l_set, vx_set, vy_set, proj_heading_set, proj_kappa_set):
+    """s_dot, l_dot and dl/ds of dynamic obstacles, 128-slot NaN-padded arrays (reference :783-808)."""
+    inp = np.array([l_set, vx_set, vy_set, proj_heading_set, proj_kappa_set], dtype=np.float64)
+    o = _runtime.planner().misc(_lib.OP_DY_OBS_DERI, inp[None], inp.shape[1], 1, (1, 3, 128))
+    return o[0, 0], o[0, 1], o[0, 2]
+
+
+def _path4(frenet_path_x, frenet_path_y, frenet_path_heading, frenet_path_kappa):
+    return np.array([frenet_path_x, frenet_path_y, frenet_path_heading, frenet_path_kappa], dtype=np.float64)
+
+
+def CalcProjPoint(s, frenet_path_x, frenet_path_y, frenet_path_heading, frenet_path_kappa, s_map):
+    """Projection of arc length s on a path given as separate arrays (reference :736-755)."""
+    o = _runtime.planner().misc(_lib.OP_CALC_PROJ_POINT, [[s], [0.0], [0.0], [0.0]], 1, 1, (4, 1),
+                                path=_path4(frenet_path_x, frenet_path_y, frenet_path_heading, frenet_path_kappa),
+                                s_map=np.asarray(s_map, dtype=np.float64))
+    return o[0, 0], o[1, 0], o[2, 0], o[3, 0]
+
+
+def Frenet2Cartesian(s_set, l_set, dl_set, ddl_set, frenet_path_x, frenet_path_y, frenet_path_heading,
+                     frenet_path_kappa, index2s):
+    """(s, l, dl, ddl) -> (x, y, heading, kappa), 600-slot NaN-padded column arrays (reference :706-733)."""
+    inp = np.array([s_set, l_set, dl_set, ddl_set], dtype=np.float64)
+    n = inp.shape[1]
+    o = _runtime.planner().misc(_lib.OP_FRENET2CART, inp, n, 1, (4, n),
+                                path=_path4(frenet_path_x, frenet_path_y, frenet_path_heading, frenet_path_kappa),
+                                s_map=np.asarray(index2s, dtype=np.float64))
+    out = [np.ones((600, 1)) * np.nan for _ in range(4)]
+    for c in range(4):
+        out[c][:n, 0] = o[c]
+    return tuple(out)

@@ -235,6 +235,32 @@ int emp_obs_cost_host(EmpPlanner *pl, const double *square_d, int n, int batch, 
 int emp_enrich_host(EmpPlanner *pl, const double *node_s, const double *node_l, const double *start, int C, int batch,
                     double resolution, int n_max, double *out_s, double *out_l, int32_t *n_out);
 
+/* ---- small S-T / speed-draft helpers (K7), host-buffer entry points -------------------------------
+ * One generic call: `op` selects the function, `in`/`out` are flat float64 arrays with the layout given below,
+ * `aux` carries the per-op side inputs.
+ *   EMP_OP_ST_GRAPH        speed_planning_test.generate_st_graph (:38-98)
+ *                          in [batch,4,n] (s,l,s_dot,l_dot), out [batch,4,n] (s_in,s_out,t_in,t_out), NaN = absent
+ *   EMP_OP_START_CONDITION speed_planning_test.calc_speed_planning_start_condition (:23-35)
+ *                          in [batch,5] (vx,vy,ax,ay,heading), out [batch,2] (s_dot, s_dot2)
+ *   EMP_OP_DY_OBS_DERI     planning_utils.cal_dy_obs_deri (:783-808)
+ *                          in [batch,5,n] (l,vx,vy,heading,kappa), out [batch,3,128] (s_dot,l_dot,dl/ds), NaN padded
+ *   EMP_OP_INDEX2S         planning_utils.trajectory_index2s (:758-780)   in [batch,2,n] (x,y), out [batch,n]
+ *   EMP_OP_ST_DP_COST      speed_planning_test.CalcDpCost (:191-231)      in [n,4] (row_start,col_start,row_end,col_end)
+ *   EMP_OP_ST_OBS_COST     speed_planning_test.CalcObsCost (:234-271)     in [n,4] (s_start,t_start,s_end,t_end)
+ *   EMP_OP_ST_COLLISION    speed_planning_test.CalcCollisionCost (:274)   in [n] min_dis, out [n]
+ *       for the three cost ops: aux.obs4 [4,n_obs] (s_in,s_out,t_in,t_out), aux.sdot_tab [40,16], aux.v0, aux.st
+ *   EMP_OP_FRENET2CART / EMP_OP_CALC_PROJ_POINT  planning_utils.Frenet2Cartesian (:706-733) / CalcProjPoint (:736-755)
+ *                          in [4,n] (s,l,dl,ddl), aux.path [4,n_nodes] (x,y,heading,kappa), aux.s_map [n_nodes], out [4,n] */
+enum { EMP_OP_ST_GRAPH = 0, EMP_OP_START_CONDITION = 1, EMP_OP_DY_OBS_DERI = 2, EMP_OP_INDEX2S = 3,
+       EMP_OP_ST_DP_COST = 4, EMP_OP_ST_OBS_COST = 5, EMP_OP_ST_COLLISION = 6, EMP_OP_FRENET2CART = 7,
+       EMP_OP_CALC_PROJ_POINT = 8 };
+typedef struct EmpMiscAux {
+    const double *obs4; int32_t n_obs; int32_t n_nodes;
+    const double *sdot_tab; const double *path; const double *s_map;
+    double v0; EmpStParams st;
+} EmpMiscAux;
+int emp_misc_host(EmpPlanner *pl, int op, const double *in, int n, int batch, const EmpMiscAux *aux, double *out);
+
 /* ---- fused planning step + all-gather over NVLink peer memory --------------------------------
  * Same as emp_sl_plan_dev, and every finished plan record is also stored into `peer_slices[r]` (r < n_peers):
  * device pointers into the OTHER GPUs' gather buffers at this rank's slice, obtained with emp_ipc_open.

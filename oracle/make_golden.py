@@ -170,8 +170,61 @@ def make_st():
     print("st done")
 
 
+def make_st_misc():
+    """Small S-T / speed-draft helpers that do run in the reference."""
+    _, pu, spt = refshim.modules()
+    from oracle import st_misc
+    rng = np.random.default_rng(scenes.BASE_SEED + 200)
+    F, n = 16, 8
+    rec = dict(dyn_s=rng.uniform(5, 40, (F, n)), dyn_l=rng.uniform(-6, 6, (F, n)), dyn_sd=rng.uniform(0, 8, (F, n)),
+               dyn_ld=rng.uniform(-2, 2, (F, n)), stg=np.zeros((F, 4, n)),
+               sc_in=rng.uniform(-3, 9, (F, 5)), sc_out=np.zeros((F, 2)),
+               deri_head=rng.uniform(-1, 1, (F, n)), deri_kap=rng.uniform(-0.02, 0.02, (F, n)),
+               deri_out=np.zeros((F, 3, 128)))
+    rec["dyn_ld"][:, 1] *= 0.1                                 # some slow lateral movers
+    for f in range(F):
+        k = int(rng.integers(2, n + 1))
+        rec["dyn_s"][f, k:] = np.nan
+        rec["dyn_l"][f, k:] = np.nan
+        rec["stg"][f] = np.array(spt.generate_st_graph(rec["dyn_s"][f], rec["dyn_l"][f], rec["dyn_sd"][f], rec["dyn_ld"][f]))
+        assert np.array_equal(rec["stg"][f], np.array(st_misc.st_graph(rec["dyn_s"][f], rec["dyn_l"][f], rec["dyn_sd"][f],
+                                                                        rec["dyn_ld"][f])), equal_nan=True)
+        rec["sc_out"][f] = spt.calc_speed_planning_start_condition(*rec["sc_in"][f])
+        rec["deri_out"][f] = np.array(pu.cal_dy_obs_deri(rec["dyn_l"][f], rec["dyn_sd"][f], rec["dyn_ld"][f],
+                                                         rec["deri_head"][f], rec["deri_kap"][f]))
+    # trajectory helpers on a curved path with NaN padding
+    xs = np.arange(0, 60, 1.0)
+    ys = 0.02 * xs ** 2
+    tx, ty = np.append(xs, [np.nan] * 4), np.append(ys, [np.nan] * 4)
+    th, kp = pu.cal_heading_kappa(list(zip(xs, ys)))
+    idx2s = pu.trajectory_index2s(tx, ty)
+    ss = np.append(np.linspace(0.7, 55, 20), [np.nan, np.nan])
+    ll = np.append(0.5 * np.sin(np.linspace(0, 3, 20)), [0, 0])
+    dl = np.append(0.05 * np.cos(np.linspace(0, 3, 20)), [0, 0])
+    ddl = np.append(-0.01 * np.sin(np.linspace(0, 3, 20)), [0, 0])
+    f2c = pu.Frenet2Cartesian(ss, ll, dl, ddl, xs, ys, np.array(th), np.array(kp), idx2s[:60])
+    rec.update(traj_x=tx, traj_y=ty, traj_s=idx2s, path_heading=np.array(th), path_kappa=np.array(kp),
+               f2c_s=ss, f2c_l=ll, f2c_dl=dl, f2c_ddl=ddl, f2c_out=np.array([a[:, 0] for a in f2c]))
+    # single-edge S-T costs
+    s_list, t_list = st_dp.S_LIST, st_dp.T_LIST
+    sc = scenes.st_scenes(1, 77)
+    obs = [sc[k][0] for k in ("s_in", "s_out", "t_in", "t_out")]
+    sdot_tab = rng.uniform(2, 12, (40, 16))
+    edges = [(0, 0, 5, 0), (3, 2, 5, 3), (0, 4, 7, 5), (20, 7, 12, 8), (39, 1, 30, 2), (10, 10, 10, 11)]
+    rec["edge_idx"] = np.array(edges)
+    rec["edge_cost"] = np.array([spt.CalcDpCost(a, b, c, d, *obs, 4000, 50, 100, 1e7, 6.5, s_list, t_list, sdot_tab)
+                                 for a, b, c, d in edges])
+    rec["edge_obs"] = np.array(obs)
+    rec["edge_sdot"] = sdot_tab
+    rec["edge_obs_cost"] = np.array([float(spt.CalcObsCost(3.0 + i, 1.0, 6.0 + 2 * i, 1.5, *obs, 1e7)) for i in range(6)])
+    rec["coll_d"] = np.array([0.0, 0.3, 0.5, 0.9, 1.4999, 1.5, 2.0, -0.7])
+    rec["coll_cost"] = np.array([spt.CalcCollisionCost(1e7, d) for d in rec["coll_d"]])
+    np.savez_compressed(os.path.join(GOLDEN, "st_misc.npz"), ref_commit=REF_COMMIT, **rec)
+    print("st_misc done")
+
+
 def main(argv):
-    what = argv or ["A", "B", "C", "frenet", "st"]
+    what = argv or ["A", "B", "C", "frenet", "st", "st_misc"]
     os.makedirs(GOLDEN, exist_ok=True)
     if "A" in what:
         make_sl("A", scenes.LATTICE_A, 0, 192)
@@ -187,6 +240,8 @@ def main(argv):
         make_frenet()
     if "st" in what:
         make_st()
+    if "st_misc" in what:
+        make_st_misc()
 
 
 if __name__ == "__main__":

@@ -73,3 +73,53 @@ def test_non_default_weights_and_dropin_signature(planner):
         sys.path.remove(pkg_dir)
         for k in [k for k in sys.modules if k == "planner" or k.startswith("planner.")]:
             del sys.modules[k]
+
+
+def test_st_helpers_dropin_against_reference_golden(planner):
+    """generate_st_graph, calc_speed_planning_start_condition, CalcDpCost/CalcObsCost/CalcCollisionCost,
+    cal_dy_obs_deri, trajectory_index2s, Frenet2Cartesian, CalcProjPoint by their reference names, against
+    outputs of the unmodified reference (tests/golden/st_misc.npz).  Tolerance 1e-9 abs / 1e-12 rel."""
+    import os, sys
+    from conftest import ROOT
+    pkg_dir = os.path.join(ROOT, "emplanner_carla_b200")
+    sys.path.insert(0, pkg_dir)
+    for k in [k for k in sys.modules if k == "planner" or k.startswith("planner.")]:
+        del sys.modules[k]
+    try:
+        from planner import speed_planning_test as spt, planning_utils as pu
+        from oracle import st_dp
+        g = load_golden("st_misc.npz")
+        for f in range(len(g["dyn_s"])):
+            got = spt.generate_st_graph(g["dyn_s"][f], g["dyn_l"][f], g["dyn_sd"][f], g["dyn_ld"][f])
+            assert np.allclose(np.array(got), g["stg"][f], rtol=1e-14, atol=0, equal_nan=True)
+            assert np.array_equal(np.isnan(np.array(got)), np.isnan(g["stg"][f]))
+            sc = spt.calc_speed_planning_start_condition(*g["sc_in"][f])
+            assert np.allclose(sc, g["sc_out"][f], rtol=0, atol=1e-12)
+            d = pu.cal_dy_obs_deri(g["dyn_l"][f], g["dyn_sd"][f], g["dyn_ld"][f], g["deri_head"][f], g["deri_kap"][f])
+            assert np.allclose(np.array(d), g["deri_out"][f], rtol=1e-13, atol=1e-13, equal_nan=True)
+        assert np.allclose(pu.trajectory_index2s(g["traj_x"], g["traj_y"]), g["traj_s"], rtol=0, atol=1e-12)
+        xs, ys = g["traj_x"][:60], g["traj_y"][:60]
+        f2c = pu.Frenet2Cartesian(g["f2c_s"], g["f2c_l"], g["f2c_dl"], g["f2c_ddl"], xs, ys, g["path_heading"],
+                                  g["path_kappa"], g["traj_s"][:60])
+        assert f2c[0].shape == (600, 1)
+        n = len(g["f2c_s"])
+        assert np.allclose(np.array([a[:n, 0] for a in f2c]), g["f2c_out"][:, :n], rtol=0, atol=1e-9, equal_nan=True)
+        px, py, ph, pk = pu.CalcProjPoint(7.3, xs, ys, g["path_heading"], g["path_kappa"], g["traj_s"][:60])
+        from oracle import st_misc
+        want = st_misc.calc_proj_point(7.3, xs, ys, g["path_heading"], g["path_kappa"], g["traj_s"][:60])
+        assert np.allclose([px, py, ph, pk], want, rtol=0, atol=1e-9)
+        obs = [g["edge_obs"][k] for k in range(4)]
+        for (a, b, c, d), want in zip(g["edge_idx"], g["edge_cost"]):
+            got = spt.CalcDpCost(int(a), int(b), int(c), int(d), *obs, 4000, 50, 100, 1e7, 6.5, st_dp.S_LIST, st_dp.T_LIST,
+                                 g["edge_sdot"])
+            assert abs(got - want) <= 1e-12 * abs(want)
+        for i, want in enumerate(g["edge_obs_cost"]):
+            got = spt.CalcObsCost(3.0 + i, 1.0, 6.0 + 2 * i, 1.5, *obs, 1e7)
+            assert abs(got - want) <= 1e-12 * max(abs(want), 1.0)
+        for dmin, want in zip(g["coll_d"], g["coll_cost"]):
+            assert abs(spt.CalcCollisionCost(1e7, dmin) - want) <= 1e-12 * max(abs(want), 1.0)
+        assert spt.CalcSTCoordinate(3, 4, st_dp.S_LIST, st_dp.T_LIST) == (st_dp.S_LIST[36], st_dp.T_LIST[4])
+    finally:
+        sys.path.remove(pkg_dir)
+        for k in [k for k in sys.modules if k == "planner" or k.startswith("planner.")]:
+            del sys.modules[k]

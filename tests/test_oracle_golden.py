@@ -155,3 +155,19 @@ def test_st_dp_against_reference_tables():
         # repaired back-track: a monotone s(t) profile ending at (min_row, min_col)
         c = o["min_col"]
         assert np.all(np.diff(o["dp_s"][:c + 1]) >= 0) and np.all(np.isnan(o["dp_s"][c + 1:]))
+
+
+def test_st_misc_oracle_against_reference_golden():
+    from oracle import st_misc
+    g = load_golden("st_misc.npz")
+    for f in range(len(g["dyn_s"])):
+        got = st_misc.st_graph(g["dyn_s"][f], g["dyn_l"][f], g["dyn_sd"][f], g["dyn_ld"][f])
+        assert np.array_equal(np.array(got), g["stg"][f], equal_nan=True)
+        assert np.array_equal(st_misc.start_condition(*g["sc_in"][f]), g["sc_out"][f])
+        d = st_misc.dy_obs_deri(g["dyn_l"][f], g["dyn_sd"][f], g["dyn_ld"][f], g["deri_head"][f], g["deri_kap"][f])
+        assert np.array_equal(np.array(d), g["deri_out"][f], equal_nan=True)
+    assert np.array_equal(st_misc.trajectory_index2s(g["traj_x"], g["traj_y"]), g["traj_s"])
+    xs, ys = g["traj_x"][:60], g["traj_y"][:60]
+    f2c = st_misc.frenet2cartesian(g["f2c_s"], g["f2c_l"], g["f2c_dl"], g["f2c_ddl"], xs, ys, g["path_heading"],
+                                   g["path_kappa"], g["traj_s"][:60])
+    assert np.allclose(np.array([a[:, 0] for a in f2c]), g["f2c_out"], rtol=0, atol=1e-12, equal_nan=True)
