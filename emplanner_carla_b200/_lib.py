@@ -40,6 +40,13 @@ class SmoothParams(C.Structure):
                 ("maxiters", C.c_int32), ("heading_only", C.c_int32)]
 
 
+class SpeedQpParams(C.Structure):
+    """EmpSpeedQpParams: speed_QP / generate_convex_space keyword defaults (speed_planning_test.py:403-404, :309)."""
+    _fields_ = [("w_s_dot2", C.c_double), ("w_v_ref", C.c_double), ("w_jerk", C.c_double),
+                ("reference_speed", C.c_double), ("max_lateral_accel", C.c_double), ("abstol", C.c_double),
+                ("reltol", C.c_double), ("feastol", C.c_double), ("maxiters", C.c_int32), ("reserved", C.c_int32)]
+
+
 class MiscAux(C.Structure):
     """EmpMiscAux: side inputs of emp_misc_host."""
     _fields_ = [("obs4", C.c_void_p), ("n_obs", C.c_int32), ("n_nodes", C.c_int32), ("sdot_tab", C.c_void_p),
@@ -75,6 +82,13 @@ _SIGNATURES = {
     "emp_st_params_default": (None, [C.POINTER(StParams)]),
     "emp_st_dp_dev": (C.c_int, [_P, C.c_int, C.c_int, C.POINTER(StParams), _P, _P, _P, _P, _P]),
     "emp_st_dp_host": (C.c_int, [_P, _P, C.c_int, C.c_int, C.POINTER(StParams), _P, _P, _P, _P]),
+    "emp_speed_qp_params_default": (None, [C.POINTER(SpeedQpParams)]),
+    "emp_st_convex_space_dev": (C.c_int, [_P, _P, C.c_int, _P, C.c_int, C.POINTER(SpeedQpParams), C.c_int, _P, _P, _P]),
+    "emp_st_speed_qp_dev": (C.c_int, [_P, _P, _P, C.c_int, C.POINTER(SpeedQpParams), _P, _P, _P]),
+    "emp_st_increase_points_dev": (C.c_int, [_P, C.c_int, _P, _P, _P]),
+    "emp_st_path_speed_merge_dev": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, _P, _P, _P]),
+    "emp_st_back_host": (C.c_int, [_P, C.c_int, C.POINTER(SpeedQpParams), _P, _P, C.c_int, _P, C.c_int, _P, _P, _P, _P,
+                                   _P, _P, C.c_int, _P, _P, _P, _P, _P, _P, _P, _P]),
     "emp_fp64_peak": (C.c_int, [C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "emp_planner_create": (C.c_int, [C.POINTER(_P), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),
     "emp_planner_destroy": (None, [_P]),
@@ -161,6 +175,15 @@ def st_params(reference_speed=50, w_cost_ref_speed=4000, w_cost_accel=100, w_cos
     p = StParams()
     p.reference_speed, p.w_ref_speed = float(reference_speed), float(w_cost_ref_speed)
     p.w_accel, p.w_obs = float(w_cost_accel), float(w_cost_obs)
+    return p
+
+
+def speed_qp_params(w_cost_s_dot2=10, w_cost_v_ref=50, w_cost_jerk=500, reference_speed=50,
+                    max_lateral_accel=0.2 * 9.8, abstol=1e-7, reltol=1e-6, feastol=1e-7, maxiters=100):
+    p = SpeedQpParams()
+    p.w_s_dot2, p.w_v_ref, p.w_jerk = float(w_cost_s_dot2), float(w_cost_v_ref), float(w_cost_jerk)
+    p.reference_speed, p.max_lateral_accel = float(reference_speed), float(max_lateral_accel)
+    p.abstol, p.reltol, p.feastol, p.maxiters = float(abstol), float(reltol), float(feastol), int(maxiters)
     return p
 
 

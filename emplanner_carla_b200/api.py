@@ -13,13 +13,15 @@ import ctypes as C
 import numpy as np
 
 from . import _lib
-from ._lib import EmpError, dp_params, qp_params, st_params, smooth_params  # noqa: F401  (re-exported)
+from ._lib import EmpError, dp_params, qp_params, st_params, smooth_params, speed_qp_params  # noqa: F401  (re-exported)
 
 PLAN_HDR = 8
 SCENE_HDR = 6
 
 DP_NO_OBSTACLE, DP_ALL_COLLIDE, DP_OVERFLOW = 1, 2, 4
 QP_OK, QP_UNKNOWN_MAXITER, QP_UNKNOWN_NUMERIC, QP_CORRIDOR_INDEX, QP_TOO_LARGE = 0, 1, 2, 4, 8
+ST_VALUE_ERROR, ST_INDEX_ERROR, ST_BAD_PROFILE = 0x10, 0x20, 0x40
+ST_COLS, ST_QP_POINTS, ST_DENSE = 16, 17, 401
 
 
 def scene_stride(kmax=8):
@@ -365,6 +367,40 @@ class HostPlanner:
             r.update(cost=cost, s_dot=sdot, node=node)
         return r
 
+    # ---- S-T back half (K8, K9) -----------------------------------------------------------------
+    def st_back(self, sq, st_out=None, scenes=None, path=None, start=None, bounds_in=None, qp_in=None, dense_in=None,
+                current_time=None, path5=None, want=("bounds", "qp")):
+        """generate_convex_space -> speed_QP -> increase_points -> path_speed_merge for a batch; `want` names the
+        outputs to return among bounds [B,4,16], qp [B,4,17], dense [B,4,401], traj [B,7,401]; stages start from
+        *_in when given.  Returns a dict with the outputs and their per-frame status arrays
+        (convex_status, qp_status, qp_iters, dense_status, merge_status)."""
+        f64 = lambda a: None if a is None else np.ascontiguousarray(a, dtype=np.float64)
+        st_out, scenes, path, start, bounds_in, qp_in, dense_in, current_time, path5 = [
+            f64(a) for a in (st_out, scenes, path, start, bounds_in, qp_in, dense_in, current_time, path5)]
+        B = next(a.shape[0] for a in (st_out, bounds_in, qp_in, dense_in) if a is not None)
+        kmax = (scenes.shape[1] - 2) // 4 if scenes is not None else 0
+        out = {}
+        if "bounds" in want:
+            out["bounds"], out["convex_status"] = np.zeros((B, 4, ST_COLS)), np.zeros(B, dtype=np.int32)
+        if "qp" in want:
+            out["qp"], out["_qsi"] = np.zeros((B, 4, ST_QP_POINTS)), np.zeros((B, 2), dtype=np.int32)
+        if "dense" in want:
+            out["dense"], out["dense_status"] = np.zeros((B, 4, ST_DENSE)), np.zeros(B, dtype=np.int32)
+        if "traj" in want:
+            out["traj"], out["merge_status"] = np.zeros((B, 7, ST_DENSE)), np.zeros(B, dtype=np.int32)
+        g = lambda k: _ptr(out[k]) if k in out else None
+        o = lambda a: _ptr(a) if a is not None else None
+        _lib.check(_lib.lib().emp_st_back_host(
+            self._h, B, C.byref(sq), o(st_out), o(scenes), kmax, o(path), path.shape[2] if path is not None else 0,
+            o(start), o(bounds_in), o(qp_in), o(dense_in), o(current_time), o(path5),
+            path5.shape[2] if path5 is not None else 0,
+            g("bounds"), g("convex_status"), g("qp"), g("_qsi"), g("dense"), g("dense_status"), g("traj"),
+            g("merge_status")))
+        if "_qsi" in out:
+            si = out.pop("_qsi")
+            out["qp_status"], out["qp_iters"] = si[:, 0].copy(), si[:, 1].copy()
+        return out
+
     @property
     def last_kernel_ms(self):
         return _lib.lib().emp_planner_last_kernel_ms(self._h)
@@ -432,6 +468,30 @@ def qp_device(scenes, qp, n_enr_max, plans, lmin_lmax=None):
     _lib.check(_lib.lib().emp_sl_qp_dev(_dev_ptr(scenes), kmax, B, C.byref(qp), int(n_enr_max), _dev_ptr(plans),
                                         _dev_ptr(lmin_lmax), _stream_ptr()))
     return plans
+
+
+def st_back_device(st_out, scenes, path, start, sq, current_time=None, path5=None):
+    """S-T back half on device tensors, four (two without path5) kernels on torch's current stream:
+    generate_convex_space -> speed_QP -> increase_points [-> path_speed_merge].  Returns a dict of CUDA tensors."""
+    import torch
+    B = st_out.shape[0]
+    kmax = (scenes.shape[1] - 2) // 4
+    dev = st_out.device
+    f64 = lambda *shape: torch.empty(shape, dtype=torch.float64, device=dev)
+    i32 = lambda *shape: torch.empty(shape, dtype=torch.int32, device=dev)
+    r = dict(bounds=f64(B, 4, ST_COLS), convex_status=i32(B), qp=f64(B, 4, ST_QP_POINTS), qp_status_iters=i32(B, 2),
+             dense=f64(B, 4, ST_DENSE), dense_status=i32(B))
+    L, sp = _lib.lib(), _stream_ptr()
+    _lib.check(L.emp_st_convex_space_dev(_dev_ptr(st_out), _dev_ptr(scenes), kmax, _dev_ptr(path), path.shape[2],
+                                         C.byref(sq), B, _dev_ptr(r["bounds"]), _dev_ptr(r["convex_status"]), sp))
+    _lib.check(L.emp_st_speed_qp_dev(_dev_ptr(start), _dev_ptr(st_out), _dev_ptr(r["bounds"]), B, C.byref(sq),
+                                     _dev_ptr(r["qp"]), _dev_ptr(r["qp_status_iters"]), sp))
+    _lib.check(L.emp_st_increase_points_dev(_dev_ptr(r["qp"]), B, _dev_ptr(r["dense"]), _dev_ptr(r["dense_status"]), sp))
+    if path5 is not None:
+        r["traj"], r["merge_status"] = f64(B, 7, ST_DENSE), i32(B)
+        _lib.check(L.emp_st_path_speed_merge_dev(_dev_ptr(r["dense"]), _dev_ptr(current_time), _dev_ptr(path5),
+                                                 path5.shape[2], B, _dev_ptr(r["traj"]), _dev_ptr(r["merge_status"]), sp))
+    return r
 
 
 def fp64_peak(iters=4096):

@@ -12,6 +12,7 @@
 #include "smooth_kernels.h"
 #include "misc_kernels.h"
 #include "st_misc_kernels.h"
+#include "st_back_kernels.h"
 
 namespace {
 
@@ -101,7 +102,7 @@ namespace {
 // Temporary device buffers for the host-buffer Frenet entry points (stream-ordered allocation).
 struct Tmp {
     cudaStream_t st;
-    void *ptrs[16];
+    void *ptrs[24];
     int n = 0;
     cudaError_t err = cudaSuccess;
     explicit Tmp(cudaStream_t s) : st(s) {}
@@ -140,6 +141,11 @@ extern "C" {
 void emp_smooth_params_default(EmpSmoothParams *p) {
     p->w_smooth = 0.4; p->w_length = 0.3; p->w_ref = 0.3; p->x_thre = 0.2; p->y_thre = 0.2;
     p->abstol = 1e-7; p->reltol = 1e-6; p->feastol = 1e-7; p->maxiters = 100; p->heading_only = 0;
+}
+
+void emp_speed_qp_params_default(EmpSpeedQpParams *p) {
+    p->w_s_dot2 = 10; p->w_v_ref = 50; p->w_jerk = 500; p->reference_speed = 50; p->max_lateral_accel = 0.2 * 9.8;
+    p->abstol = 1e-7; p->reltol = 1e-6; p->feastol = 1e-7; p->maxiters = 100; p->reserved = 0;
 }
 
 void emp_st_params_default(EmpStParams *p) {
@@ -757,6 +763,125 @@ int emp_misc_host(EmpPlanner *pl, int op, const double *in, int n, int batch, co
         if (t.err != cudaSuccess) return fail_cuda(t.err, "misc copy-back");
     }
     EMP_CK(cudaStreamSynchronize(pl->stream), "planner stream");
+    return 0;
+}
+
+int emp_st_convex_space_dev(const double *st_out, const double *scenes, int kmax, const double *path, int n_path,
+                            const EmpSpeedQpParams *p, int batch, double *bounds, int32_t *status, void *stream) {
+    if (!p) return fail(-1, "EmpSpeedQpParams is NULL");
+    if (kmax < 0 || kmax > EMP_ST_KMAX || (kmax & 1)) return fail(-2, "kmax must be even and in [0, 16]");
+    if (batch < 0 || n_path < 1) return fail(-2, "bad batch / n_path");
+    if (batch == 0) return 0;
+    if (!st_out || !scenes || !path || !bounds || !status) return fail(-1, "NULL argument");
+    cudaError_t e = emp::launch_convex_space(st_out, scenes, kmax, path, n_path, p->max_lateral_accel, batch, bounds,
+                                             status, (cudaStream_t)stream);
+    return e == cudaSuccess ? 0 : fail_cuda(e, "convex_space launch");
+}
+
+int emp_st_speed_qp_dev(const double *start, const double *st_out, const double *bounds, int batch,
+                        const EmpSpeedQpParams *p, double *qp, int32_t *status_iters, void *stream) {
+    if (!p) return fail(-1, "EmpSpeedQpParams is NULL");
+    if (batch < 0) return fail(-2, "bad batch");
+    if (batch == 0) return 0;
+    if (!start || !st_out || !bounds || !qp || !status_iters) return fail(-1, "NULL argument");
+    emp::SpeedQpLaunch L{*p, batch};
+    cudaError_t e = emp::launch_speed_qp(start, st_out, bounds, qp, status_iters, L, (cudaStream_t)stream);
+    return e == cudaSuccess ? 0 : fail_cuda(e, "speed_qp launch");
+}
+
+int emp_st_increase_points_dev(const double *qp, int batch, double *dense, int32_t *status, void *stream) {
+    if (batch < 0) return fail(-2, "bad batch");
+    if (batch == 0) return 0;
+    if (!qp || !dense || !status) return fail(-1, "NULL argument");
+    cudaError_t e = emp::launch_increase_points(qp, batch, dense, status, (cudaStream_t)stream);
+    return e == cudaSuccess ? 0 : fail_cuda(e, "increase_points launch");
+}
+
+int emp_st_path_speed_merge_dev(const double *dense, const double *current_time, const double *path5, int n_path,
+                                int batch, double *traj, int32_t *status, void *stream) {
+    if (batch < 0 || n_path < 1) return fail(-2, "bad batch / n_path");
+    if (batch == 0) return 0;
+    if (!dense || !current_time || !path5 || !traj || !status) return fail(-1, "NULL argument");
+    cudaError_t e = emp::launch_path_speed_merge(dense, current_time, path5, n_path, batch, traj, status,
+                                                 (cudaStream_t)stream);
+    return e == cudaSuccess ? 0 : fail_cuda(e, "path_speed_merge launch");
+}
+
+int emp_st_back_host(EmpPlanner *pl, int batch, const EmpSpeedQpParams *p,
+                     const double *st_out, const double *scenes, int kmax, const double *path, int n_path,
+                     const double *start, const double *bounds_in, const double *qp_in, const double *dense_in,
+                     const double *current_time, const double *path5, int n_path5,
+                     double *bounds, int32_t *convex_status, double *qp, int32_t *qp_status_iters,
+                     double *dense, int32_t *dense_status, double *traj, int32_t *merge_status) {
+    if (!pl || !p) return fail(-1, "NULL argument");
+    if (batch <= 0) return batch == 0 ? 0 : fail(-2, "bad batch");
+    // which stages run: a stage runs when its output is wanted or a later stage needs it and no *_in replaces it
+    const bool want_merge = traj != nullptr;
+    const bool run_dense = (dense != nullptr || (want_merge && !dense_in));
+    const bool run_qp = (qp != nullptr || (run_dense && !qp_in)) && !(qp_in && !qp);
+    const bool run_convex = (bounds != nullptr || (run_qp && !bounds_in)) && !(bounds_in && !bounds);
+    if (run_convex && (!st_out || !scenes || !path)) return fail(-1, "convex space needs st_out, scenes and path");
+    if (run_qp && (!st_out || !start)) return fail(-1, "speed QP needs st_out and start");
+    if (run_dense && !run_qp && !qp_in) return fail(-1, "increase_points needs a QP result");
+    if (want_merge && (!current_time || !path5)) return fail(-1, "path_speed_merge needs current_time and path5");
+    EMP_CK(cudaSetDevice(pl->device), "cudaSetDevice");
+    const size_t B = batch;
+    int rc = 0;
+    {
+        Tmp t(pl->stream);
+        const double *d_st = (run_convex || run_qp) ? t.in(st_out, B * EMP_ST_OUT_STRIDE) : nullptr;
+        const double *d_bnd = bounds_in ? t.in(bounds_in, B * 4 * EMP_ST_COLS) : nullptr;
+        const double *d_qp = qp_in ? t.in(qp_in, B * 4 * EMP_ST_QP_POINTS) : nullptr;
+        const double *d_dense = dense_in ? t.in(dense_in, B * 4 * EMP_ST_DENSE) : nullptr;
+        int32_t *d_cs = nullptr, *d_qs = nullptr, *d_ds = nullptr, *d_ms = nullptr;
+        double *d_traj = nullptr;
+        if (run_convex) {
+            const double *d_sc = t.in(scenes, B * (2 + 4 * kmax));
+            const double *d_path = t.in(path, B * 2 * n_path);
+            double *o = t.out<double>(B * 4 * EMP_ST_COLS);
+            d_cs = t.out<int32_t>(B);
+            if (t.err != cudaSuccess) return fail_cuda(t.err, "st_back staging");
+            rc = emp_st_convex_space_dev(d_st, d_sc, kmax, d_path, n_path, p, batch, o, d_cs, pl->stream);
+            if (rc) return rc;
+            d_bnd = o;
+        }
+        if (run_qp) {
+            const double *d_start = t.in(start, B * 2);
+            double *o = t.out<double>(B * 4 * EMP_ST_QP_POINTS);
+            d_qs = t.out<int32_t>(B * 2);
+            if (t.err != cudaSuccess) return fail_cuda(t.err, "st_back staging");
+            EMP_CK(cudaEventRecord(pl->ev0, pl->stream), "event");
+            rc = emp_st_speed_qp_dev(d_start, d_st, d_bnd, batch, p, o, d_qs, pl->stream);
+            EMP_CK(cudaEventRecord(pl->ev1, pl->stream), "event");
+            if (rc) return rc;
+            d_qp = o;
+        }
+        if (run_dense) {
+            double *o = t.out<double>(B * 4 * EMP_ST_DENSE);
+            d_ds = t.out<int32_t>(B);
+            if (t.err != cudaSuccess) return fail_cuda(t.err, "st_back staging");
+            rc = emp_st_increase_points_dev(d_qp, batch, o, d_ds, pl->stream);
+            if (rc) return rc;
+            d_dense = o;
+        }
+        if (want_merge) {
+            if (!d_dense) return fail(-1, "path_speed_merge needs a densified profile");
+            const double *d_now = t.in(current_time, B);
+            const double *d_p5 = t.in(path5, B * 5 * n_path5);
+            d_traj = t.out<double>(B * 7 * EMP_ST_DENSE);
+            d_ms = t.out<int32_t>(B);
+            if (t.err != cudaSuccess) return fail_cuda(t.err, "st_back staging");
+            rc = emp_st_path_speed_merge_dev(d_dense, d_now, d_p5, n_path5, batch, d_traj, d_ms, pl->stream);
+            if (rc) return rc;
+        }
+        if (run_convex) { t.back(bounds, d_bnd, B * 4 * EMP_ST_COLS); t.back(convex_status, d_cs, B); }
+        if (run_qp) { t.back(qp, d_qp, B * 4 * EMP_ST_QP_POINTS); t.back(qp_status_iters, d_qs, B * 2); }
+        if (run_dense) { t.back(dense, d_dense, B * 4 * EMP_ST_DENSE); t.back(dense_status, d_ds, B); }
+        if (want_merge) { t.back(traj, d_traj, B * 7 * EMP_ST_DENSE); t.back(merge_status, d_ms, B); }
+        if (t.err != cudaSuccess) return fail_cuda(t.err, "st_back copy-back");
+    }
+    EMP_CK(cudaStreamSynchronize(pl->stream), "planner stream");
+    if (run_qp) cudaEventElapsedTime(&pl->last_ms, pl->ev0, pl->ev1);
     return 0;
 }
 

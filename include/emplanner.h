@@ -39,6 +39,8 @@ extern "C" {
 #define EMP_ST_ROWS 40           /* s samples of the S-T lattice, speed_planning_test.py:114 */
 #define EMP_ST_COLS 16           /* t samples (0.5 s), speed_planning_test.py:116 */
 #define EMP_ST_OUT_STRIDE 40     /* words per S-T result record */
+#define EMP_ST_QP_POINTS 17      /* output length of speed_QP, speed_planning_test.py:422 */
+#define EMP_ST_DENSE 401         /* output length of increase_points / path_speed_merge, :541, :571 */
 
 /* ---- per-frame status bits ------------------------------------------------ */
 #define EMP_DP_NO_OBSTACLE      0x1   /* K == 0: straight branch, path_planning.py:362-363 */
@@ -49,6 +51,9 @@ extern "C" {
 #define EMP_QP_UNKNOWN_NUMERIC  2     /* 'unknown': factorisation breakdown / non-finite iterate */
 #define EMP_QP_CORRIDOR_INDEX   4     /* cal_lmin_lmax would raise IndexError, path_planning.py:265-272 */
 #define EMP_QP_TOO_LARGE        8     /* more than EMP_MAX_QP_POINTS stations, or fewer than 2 */
+#define EMP_ST_VALUE_ERROR      0x10  /* the reference raises ValueError (scipy interp1d out of range, empty table) */
+#define EMP_ST_INDEX_ERROR      0x20  /* the reference raises IndexError (S-T profile without NaN terminator, index 16) */
+#define EMP_ST_BAD_PROFILE      0x40  /* S-T profile with fewer than 2 valid points: nothing to smooth */
 
 /* ---- parameters (defaults = the reference's keyword defaults) -------------- */
 typedef struct EmpDpParams {          /* DP_algorithm, path_planning.py:276-279 */
@@ -89,6 +94,16 @@ typedef struct EmpSmoothParams {      /* smooth_reference_line, planning_utils.p
     int32_t heading_only;             /* 1: skip the QP, output cal_heading_kappa (:185-228) of the input polyline */
 } EmpSmoothParams;
 
+typedef struct EmpSpeedQpParams {     /* speed_QP :403-404, generate_convex_space :309, cvxopt defaults */
+    double w_s_dot2, w_v_ref, w_jerk; /* 10, 50, 500 */
+    double reference_speed;           /* 50 */
+    double max_lateral_accel;         /* 0.2 * 9.8 */
+    double abstol, reltol, feastol;   /* 1e-7, 1e-6, 1e-7 */
+    int32_t maxiters;                 /* 100 */
+    int32_t reserved;
+} EmpSpeedQpParams;
+
+void emp_speed_qp_params_default(EmpSpeedQpParams *p);
 void emp_smooth_params_default(EmpSmoothParams *p);
 void emp_st_params_default(EmpStParams *p);
 void emp_dp_params_default(EmpDpParams *p);
@@ -217,6 +232,41 @@ int emp_st_dp_dev(const double *scenes, int kmax, int batch, const EmpStParams *
                   double *cost_tab, double *sdot_tab, int32_t *node_tab, void *stream);
 int emp_st_dp_host(EmpPlanner *pl, const double *scenes, int kmax, int batch, const EmpStParams *p, double *out,
                    double *cost_tab, double *sdot_tab, int32_t *node_tab);
+
+/* ---- S-T back half (K8, K9) ---------------------------------------------------------------
+ * st_out: the [batch, EMP_ST_OUT_STRIDE] records emp_st_dp_dev wrote (dp_speed_s at word 8, dp_speed_t at word 24);
+ * scenes: the same S-T scene records.  Per-frame status: 0, or EMP_ST_VALUE_ERROR / EMP_ST_INDEX_ERROR /
+ * EMP_ST_BAD_PROFILE where the reference would raise (the drop-in wrappers re-raise).
+ *
+ * emp_st_convex_space_dev: speed_planning_test.generate_convex_space (:308-400).
+ *   path [batch,2,n_path] = (path_index2s, trajectory_kappa_init), index2s zero padded (planning_utils.trajectory_index2s);
+ *   bounds [batch,4,16] = (s_lb, s_ub, s_dot_lb, s_dot_ub), +-inf where unbounded; status [batch].
+ * emp_st_speed_qp_dev: speed_planning_test.speed_QP (:403-511, incl. cvxopt.solvers.qp :502) with the two repairs
+ *   the draft needs to run at all (equality matrix transposed; lb/ub as two arrays whose finite entries become
+ *   inequality rows - oracle/st_back.py).  start [batch,2] = (plan_start_s_dot, plan_start_s_dot2);
+ *   qp [batch,4,17] = (qp_s, qp_s_dot, qp_s_dot2, relative_time), NaN beyond qp_size; status_iters [batch,2].
+ * emp_st_increase_points_dev: speed_planning_test.increase_points (:514-562).  qp [batch,4,17] -> dense [batch,4,401]
+ *   = (s, s_dot, s_dot2, relative_time).
+ * emp_st_path_speed_merge_dev: speed_planning_test.path_speed_merge (:565-611).  path5 [batch,5,n_path] = (path_s,
+ *   trajectory_x/y/heading/kappa_init), x NaN padded; current_time [batch]; traj [batch,7,401] = (x, y, heading,
+ *   kappa, speed, accel, time). */
+int emp_st_convex_space_dev(const double *st_out, const double *scenes, int kmax, const double *path, int n_path,
+                            const EmpSpeedQpParams *p, int batch, double *bounds, int32_t *status, void *stream);
+int emp_st_speed_qp_dev(const double *start, const double *st_out, const double *bounds, int batch,
+                        const EmpSpeedQpParams *p, double *qp, int32_t *status_iters, void *stream);
+int emp_st_increase_points_dev(const double *qp, int batch, double *dense, int32_t *status, void *stream);
+int emp_st_path_speed_merge_dev(const double *dense, const double *current_time, const double *path5, int n_path,
+                                int batch, double *traj, int32_t *status, void *stream);
+/* Host-buffer versions.  Any output pointer may be NULL; a stage whose inputs are missing is an argument error.
+ * emp_st_back_host chains convex space -> speed QP -> increase_points -> path_speed_merge for the stages whose
+ * outputs (or successors' outputs) are requested, starting from caller-supplied intermediate results when given:
+ *   bounds_in [batch,4,16] (skip convex space), qp_in [batch,4,17] (skip the QP), dense_in [batch,4,401]. */
+int emp_st_back_host(EmpPlanner *pl, int batch, const EmpSpeedQpParams *p,
+                     const double *st_out, const double *scenes, int kmax, const double *path, int n_path,
+                     const double *start, const double *bounds_in, const double *qp_in, const double *dense_in,
+                     const double *current_time, const double *path5, int n_path5,
+                     double *bounds, int32_t *convex_status, double *qp, int32_t *qp_status_iters,
+                     double *dense, int32_t *dense_status, double *traj, int32_t *merge_status);
 
 /* ---- stand-alone pieces of the S-L DP (K6), host-buffer entry points ------------------------------
  * emp_quintic_host:   planning_utils.cal_quintic_coefficient (:671-703).  in [n,8] = (start_l, start_dl, start_ddl,

@@ -223,8 +223,111 @@ def make_st_misc():
     print("st_misc done")
 
 
+def st_back_path(f, n_pad=3):
+    """Per-frame synthetic planned path for the S-T back half: 1 m spaced parabola with frame-dependent curvature,
+    NaN padded like the reference's fixed-size trajectory buffers (test_10.py:228-262)."""
+    n_valid = 45 if f % 8 == 3 else 90                     # short paths: interp1d ValueError at :341
+    xs = np.arange(0, 90, 1.0)
+    ys = (0.001 + 0.0005 * (f % 7)) * xs ** 2 * (1 if f % 2 else -1)
+    return xs[:n_valid], ys[:n_valid], n_pad + 90 - n_valid
+
+
+def make_st_back(n_frames=128, n_dense=6):
+    """S-T back half: generate_convex_space / increase_points / path_speed_merge outputs of the unmodified
+    reference, everything speed_QP builds before its (failing) solver call, and the repaired solve (oracle)."""
+    _, pu, spt = refshim.modules()
+    from oracle import st_back
+    sc = scenes.st_scenes(n_frames, 5, k_fixed=None)
+    F = n_frames
+    sc["t_out"][5::16, 0] = np.where(np.isnan(sc["t_out"][5::16, 0]), np.nan, 7.6)   # late exit: dp_speed_t[16], :391
+    rec = dict(dp_s=np.zeros((F, 16)), dp_t=np.zeros((F, 16)), a0=_rng_a0(F), ref_bounds=np.full((F, 4, 16), np.nan),
+               ref_convex_exc=np.zeros(F, np.int32), qp=np.full((F, 4, 17), np.nan), qp_optimal=np.zeros(F, np.int32),
+               qp_iters=np.zeros(F, np.int32), qp_exc=np.zeros(F, np.int32), matrices_identical=np.zeros(F, np.int32))
+    dense_frames, ref_dense, ref_traj, paths, path5s = [], [], [], [], []
+    EXC = {IndexError: 0x20, ValueError: 0x10}
+
+    class Captured(Exception):
+        pass
+
+    cap = {}
+
+    def fake_qp(*a, **k):
+        cap["args"] = [np.array(np.asarray(x)) for x in a]
+        raise Captured()
+
+    for f in range(F):
+        o = st_dp.speed_dp(sc["s_in"][f], sc["s_out"][f], sc["t_in"][f], sc["t_out"][f], sc["v0"][f])
+        dp_s, dp_t = o["dp_s"], o["dp_t"]
+        rec["dp_s"][f], rec["dp_t"][f] = dp_s, dp_t
+        xs, ys, n_pad = st_back_path(f)
+        th, kp = pu.cal_heading_kappa(list(zip(xs, ys)))
+        pad = [np.nan] * n_pad
+        tx, ty = np.append(xs, pad), np.append(ys, pad)
+        idx2s = np.asarray(pu.trajectory_index2s(tx, ty))
+        kap = np.append(np.array(kp), [0.0] * n_pad)
+        paths.append(np.array([idx2s, kap]))
+        path5s.append(np.array([idx2s, tx, ty, np.append(th, pad), np.append(kp, pad)]))
+        args = (dp_s, dp_t, idx2s, sc["s_in"][f], sc["s_out"][f], sc["t_in"][f], sc["t_out"][f], kap)
+        try:
+            cs = spt.generate_convex_space(*args)
+            rec["ref_bounds"][f] = np.array(cs)
+        except (IndexError, ValueError) as e:
+            rec["ref_convex_exc"][f] = EXC[type(e)]
+            cs = None
+        try:
+            mine = st_back.convex_space(*args)
+            assert cs is not None and all(np.array_equal(a, b) for a, b in zip(cs, mine)), f
+        except (IndexError, ValueError) as e:
+            assert rec["ref_convex_exc"][f] == EXC[type(e)], f
+        if cs is None:
+            continue
+        a0 = rec["a0"][f]
+        old = spt.cvxopt.solvers.qp
+        spt.cvxopt.solvers.qp = fake_qp
+        try:
+            spt.speed_QP(sc["v0"][f], a0, dp_s, dp_t, *cs)
+            raise AssertionError("reference speed_QP returned")
+        except Captured:
+            m = st_back.speed_qp_matrices(sc["v0"][f], a0, dp_s, dp_t, *cs)
+            same = all(np.array_equal(x, m[k].reshape(x.shape)) for x, k in zip(cap["args"], ("H", "f", "A", "b", "Aeq", "beq")))
+            assert same, f
+            rec["matrices_identical"][f] = 1
+        except IndexError:
+            rec["qp_exc"][f] = EXC[IndexError]
+            try:
+                st_back.speed_qp_matrices(sc["v0"][f], a0, dp_s, dp_t, *cs)
+                raise AssertionError("oracle did not raise")
+            except IndexError:
+                pass
+            continue
+        finally:
+            spt.cvxopt.solvers.qp = old
+        r = st_back.speed_qp(sc["v0"][f], a0, dp_s, dp_t, *cs)
+        rec["qp"][f] = np.array(r[:4])
+        rec["qp_optimal"][f] = int(r[4]["status"] == "optimal")
+        rec["qp_iters"][f] = r[4]["iterations"]
+        if len(dense_frames) < n_dense:
+            ip = spt.increase_points(*r[:4])
+            assert all(np.array_equal(a, b) for a, b in zip(ip, st_back.increase_points(*r[:4])))
+            mg = spt.path_speed_merge(*ip, 12.5 + f, *path5s[-1])
+            assert all(np.array_equal(a, b, equal_nan=True) for a, b in zip(mg, st_back.path_speed_merge(*ip, 12.5 + f, *path5s[-1])))
+            dense_frames.append(f)
+            ref_dense.append(np.array(ip))
+            ref_traj.append(np.array(mg))
+        print("st_back", f, "q=%d" % m["qp_size"], r[4]["status"], r[4]["iterations"], flush=True)
+    rec.update(path=np.array(paths), path5=np.array(path5s), dense_frames=np.array(dense_frames),
+               ref_dense=np.array(ref_dense), ref_traj=np.array(ref_traj), current_time=12.5 + np.arange(F))
+    np.savez_compressed(os.path.join(GOLDEN, "st_back.npz"), ref_commit=REF_COMMIT, **sc, **rec)
+    print("st_back done: %d convex ok, %d QPs (%d optimal)" % (int((rec["ref_convex_exc"] == 0).sum()),
+          int(rec["matrices_identical"].sum()), int(rec["qp_optimal"].sum())))
+
+
+def _rng_a0(n):
+    return np.random.default_rng(scenes.BASE_SEED + 300).uniform(-1.0, 1.0, n)
+
+
 def main(argv):
-    what = argv or ["A", "B", "C", "frenet", "st", "st_misc"]
+    what = argv or ["A", "B", "C", "frenet", "st", "st_misc", "st_back"]
     os.makedirs(GOLDEN, exist_ok=True)
     if "A" in what:
         make_sl("A", scenes.LATTICE_A, 0, 192)
@@ -242,6 +345,8 @@ def main(argv):
         make_st()
     if "st_misc" in what:
         make_st_misc()
+    if "st_back" in what:
+        make_st_back()
 
 
 if __name__ == "__main__":

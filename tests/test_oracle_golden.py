@@ -171,3 +171,50 @@ def test_st_misc_oracle_against_reference_golden():
     f2c = st_misc.frenet2cartesian(g["f2c_s"], g["f2c_l"], g["f2c_dl"], g["f2c_ddl"], xs, ys, g["path_heading"],
                                    g["path_kappa"], g["traj_s"][:60])
     assert np.allclose(np.array([a[:, 0] for a in f2c]), g["f2c_out"], rtol=0, atol=1e-12, equal_nan=True)
+
+
+def test_st_back_oracle_against_reference_golden():
+    """oracle/st_back.py vs outputs of the unmodified reference (generate_convex_space incl. its exceptions,
+    increase_points, path_speed_merge: bit-exact) and vs the stored repaired speed_QP solve."""
+    from oracle import st_back
+    g = load_golden("st_back.npz")
+    EXC = {IndexError: 0x20, ValueError: 0x10}
+    n_qp = 0
+    for f in range(len(g["v0"])):
+        args = (g["dp_s"][f], g["dp_t"][f], g["path"][f, 0], g["s_in"][f], g["s_out"][f], g["t_in"][f], g["t_out"][f],
+                g["path"][f, 1])
+        try:
+            cs = st_back.convex_space(*args)
+            assert g["ref_convex_exc"][f] == 0 and np.array_equal(np.array(cs), g["ref_bounds"][f])
+        except (IndexError, ValueError) as e:
+            assert g["ref_convex_exc"][f] == EXC[type(e)]
+            continue
+        if g["matrices_identical"][f] and n_qp < 6:
+            r = st_back.speed_qp(g["v0"][f], g["a0"][f], g["dp_s"][f], g["dp_t"][f], *cs)
+            assert np.array_equal(np.array(r[:4]), g["qp"][f], equal_nan=True)
+            assert r[4]["iterations"] == g["qp_iters"][f] and (r[4]["status"] == "optimal") == bool(g["qp_optimal"][f])
+            n_qp += 1
+        elif g["qp_exc"][f]:
+            with pytest.raises(IndexError):
+                st_back.speed_qp_matrices(g["v0"][f], g["a0"][f], g["dp_s"][f], g["dp_t"][f], *cs)
+    assert n_qp == 6
+    for k, f in enumerate(g["dense_frames"]):
+        ip = st_back.increase_points(*g["qp"][f])
+        assert np.array_equal(np.array(ip), g["ref_dense"][k])
+        mg = st_back.path_speed_merge(*ip, g["current_time"][f], *g["path5"][f])
+        assert np.array_equal(np.array(mg), g["ref_traj"][k], equal_nan=True)
+
+
+def test_speed_qp_repair_is_a_valid_qp_solution():
+    """KKT check of the repaired speed_QP on a golden frame: primal feasibility of Aeq' x = 0, bounds, and that no
+    feasible perturbation along the null space lowers the objective (first-order optimality)."""
+    from oracle import st_back
+    g = load_golden("st_back.npz")
+    f = int(np.nonzero((g["matrices_identical"] == 1) & (g["qp_optimal"] == 1))[0][0])
+    m = st_back.speed_qp_matrices(g["v0"][f], g["a0"][f], g["dp_s"][f], g["dp_t"][f], *g["ref_bounds"][f])
+    P, q, G, h, A, b = st_back.speed_qp_cone_form(m)
+    r = st_back.speed_qp(g["v0"][f], g["a0"][f], g["dp_s"][f], g["dp_t"][f], *g["ref_bounds"][f])
+    x, info = r[4]["x"], r[4]
+    assert np.abs(A @ x - b).max() < 1e-6 and (G @ x - h).max() < 1e-6
+    assert np.abs(P @ x + q + A.T @ info["y"] + G.T @ info["z"]).max() < 1e-4 * max(1.0, np.abs(q).max())
+    assert info["z"].min() > -1e-9 and abs(info["z"] @ (h - G @ x)) < 1e-5 * abs(info["pcost"])   # reltol 1e-6
