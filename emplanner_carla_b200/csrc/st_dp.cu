@@ -11,14 +11,144 @@
 //   * an edge whose start ROW is 0 is treated as starting from the DP origin (s=0, t=0, plan_start_s_dot) (:208-212);
 //   * the 5 obstacle samples of an edge sit at t_start + (i-1)*dt, i = 0..4 (:251-252);
 //   * the end-node scans use '<=' so the last minimum wins (:163,:169).
-// Arithmetic follows oracle/st_dp.py's association order; compiled with -fmad=false.  pow() may differ from
-// glibc's by an ulp, so costs are compared at 1e-12 relative, parents exactly.
+// Arithmetic follows oracle/st_dp.py's association order; compiled with -fmad=false.  w^y is evaluated as
+// exp(y ln w) with ln w in double-double (a few ulp, like pow()), so costs are compared at 1e-12 relative,
+// parents exactly.
+//
+// Work layout.  An edge costs 5 samples x K obstacles point-to-segment distances, but only ~10 % of those
+// (sample, obstacle) pairs lie within 1.5 of the obstacle's S-T segment and cost anything.  One lane per edge
+// with the distance code inline ran at 13 of 32 lanes active (ncu, profiles/r1_st_v1_summary.txt).  Now:
+//   * per frame, for every (column, sample, obstacle) the s-interval in which a sample at that column's sample
+//     time can be within 1.6 of the segment is tabulated once (the sample times of a column are shared by all
+//     its edges) - the per-pair test is two comparisons;
+//   * the pairs that pass are compacted through a 64-slot ring per warp; whenever 32 are pending the warp
+//     evaluates them with all lanes busy (reference arithmetic, operands fetched from the owning lane by
+//     shuffle) and each owner adds its results in (sample, obstacle) order, so the sums stay bit-identical.
 #include "emp_common.cuh"
 #include "st_kernels.h"
 #include "st_device.cuh"
 
 namespace emp {
 namespace {
+
+constexpr int ST_WARPS = ST_THREADS / 32;
+constexpr double NEAR_R = 1.6;        // > 1.5: beyond it CalcCollisionCost returns exactly 0 (margin covers rounding)
+
+struct Interval { double lo, hi; };
+
+// s-range of the horizontal line t = T inside the capsule of radius NEAR_R around the segment (s1,t1)-(s2,t2)
+__device__ Interval capsule_slice(double s1, double t1, double s2, double t2, double T) {
+    const double INF = __longlong_as_double(0x7ff0000000000000LL);
+    double lo = INF, hi = -INF;
+    const double d1 = T - t1, d2 = T - t2, R2 = NEAR_R * NEAR_R;
+    if (fabs(d1) < NEAR_R) { const double w = sqrt(R2 - d1 * d1); lo = fmin(lo, s1 - w); hi = fmax(hi, s1 + w); }
+    if (fabs(d2) < NEAR_R) { const double w = sqrt(R2 - d2 * d2); lo = fmin(lo, s2 - w); hi = fmax(hi, s2 + w); }
+    const double ds = s2 - s1, dtt = t2 - t1, len2 = ds * ds + dtt * dtt;
+    if (dtt != 0.0) {
+        const double sc = s1 + d1 * ds / dtt, hw = NEAR_R * sqrt(len2) / fabs(dtt);
+        double a = sc - hw, b = sc + hw;
+        bool ok = true;
+        if (ds != 0.0) {
+            const double u0 = s1 - d1 * dtt / ds, u1 = s1 + (len2 - d1 * dtt) / ds;
+            a = fmax(a, fmin(u0, u1));
+            b = fmin(b, fmax(u0, u1));
+        } else {
+            const double u = d1 / dtt;
+            ok = u >= 0.0 && u <= 1.0;
+        }
+        if (ok && a <= b) { lo = fmin(lo, a); hi = fmax(hi, b); }
+    } else if (fabs(d1) < NEAR_R) {
+        lo = fmin(lo, fmin(s1, s2) - NEAR_R);
+        hi = fmax(hi, fmax(s1, s2) + NEAR_R);
+    }
+    if (lo <= hi) { lo -= 1e-9 * (1.0 + fabs(lo)); hi += 1e-9 * (1.0 + fabs(hi)); }
+    return Interval{lo, hi};
+}
+
+// CalcObsCost's per-sample, per-obstacle term (:253-269) in the reference's arithmetic order
+__device__ __forceinline__ double point_cost(double s, double t, const Obs o, double w_obs, double lnw_hi, double lnw_lo) {
+    const double v1s = o.s_in - s, v1t = o.t_in - t;
+    const double v2s = o.s_out - s, v2t = o.t_out - t;
+    const double v3s = v2s - v1s, v3t = v2t - v1t;
+    const double d13 = v1s * v3s + v1t * v3t;
+    const double d23 = v2s * v3s + v2t * v3t;
+    const bool ends = (d13 > 0 && d23 > 0) || (d13 < 0 && d23 < 0);
+    // sqrt is monotone and correctly rounded: min(sqrt a, sqrt b) = sqrt(min(a, b))
+    const double num = ends ? fmin(v1s * v1s + v1t * v1t, v2s * v2s + v2t * v2t) : v3s * v3s + v3t * v3t;
+    const double root = sqrt(num);
+    const double dmin = ends ? root : fabs(v1s * v3t - v1t * v3s) / root;
+    const double ad = fabs(dmin);
+    if (ad < 0.5) return w_obs;
+    if (0.5 < ad && ad < 1.5) {
+        const double y = (0.5 - dmin) + 1;                 // w_obs ** y
+        const double ph = y * lnw_hi;
+        const double pl = fma(y, lnw_hi, -ph) + y * lnw_lo;
+        const double e = exp(ph);
+        return fma(e, pl, e);
+    }
+    return 0.0;
+}
+
+struct WarpRing {
+    double val[64];
+    uint32_t desc[64];
+};
+
+// Obstacle cost (CalcObsCost :234-271) of one edge per lane, for a warp's 32 edges at once.
+__device__ __forceinline__ double warp_obs_cost(bool valid, double s_st, double t_st, double s_en, double t_en,
+                                                const Interval *tab /* [NSAMP][kmax] of this lane's edge kind */,
+                                                int kmax, const Obs *obs, int n_act, WarpRing &ring, double w_obs,
+                                                double lnw_hi, double lnw_lo, int lane) {
+    const double dt = (t_en - t_st) / (NSAMP - 1);
+    const double k = (s_en - s_st) / (t_en - t_st);
+    double cost = 0.0;
+    unsigned long long mine = 0ull;                        // ring slots holding this lane's pending pairs
+    int head = 0, count = 0;                               // warp-uniform
+    auto flush = [&](int n) {
+        __syncwarp();
+        const uint32_t d = ring.desc[(head + lane) & 63];
+        const bool have = lane < n;
+        const int ol = have ? (int)(d & 31u) : lane, i = (int)((d >> 5) & 7u), j = (int)(d >> 8);
+        const double os = shfl(s_st, ol), ot = shfl(t_st, ol), oe = shfl(s_en, ol);
+        if (have) {
+            const double odt = (t_en - ot) / (NSAMP - 1);
+            const double ok = (oe - os) / (t_en - ot);
+            const double t = ot + (double)(i - 1) * odt;               // sic: samples at (i-1)*dt (:251-252)
+            const double s = os + (ok * (double)(i - 1)) * odt;
+            ring.val[(head + lane) & 63] = point_cost(s, t, obs[j], w_obs, lnw_hi, lnw_lo);
+        }
+        __syncwarp();
+        unsigned long long m = ((mine >> head) | (head ? mine << (64 - head) : 0ull)) & ((n >= 64) ? ~0ull : ((1ull << n) - 1ull));
+        while (m) {                                        // own results, in (sample, obstacle) order
+            const int p = __ffsll((long long)m) - 1;
+            cost = cost + ring.val[(head + p) & 63];
+            mine &= ~(1ull << ((head + p) & 63));
+            m &= m - 1;
+        }
+        head = (head + n) & 63;
+        count -= n;
+    };
+#pragma unroll 1
+    for (int i = 0; i < NSAMP; ++i) {
+        const double s = s_st + (k * (double)(i - 1)) * dt;
+        for (int j = 0; j < n_act; ++j) {
+            const Interval iv = tab[i * kmax + j];
+            const bool near = valid && iv.lo <= s && s <= iv.hi;
+            const unsigned b = __ballot_sync(EMP_FULL_MASK, near);
+            if (b) {
+                if (near) {
+                    const int pos = (head + count + __popc(b & ((1u << lane) - 1u))) & 63;
+                    ring.desc[pos] = (uint32_t)lane | ((uint32_t)i << 5) | ((uint32_t)j << 8);
+                    mine |= 1ull << pos;
+                }
+                count += __popc(b);
+                if (count >= 32) flush(32);
+            }
+        }
+    }
+    if (count > 0) flush(count);
+    return cost;
+}
 
 __global__ void __launch_bounds__(ST_THREADS)
 st_dp_kernel(const double *__restrict__ scenes, double *__restrict__ out, double *__restrict__ cost_tab,
@@ -28,45 +158,91 @@ st_dp_kernel(const double *__restrict__ scenes, double *__restrict__ out, double
     __shared__ unsigned char node_sm[NCOL][NROW];
     __shared__ Obs obs[EMP_ST_KMAX];
     __shared__ double top_cost[NCOL];
-    const int frame = blockIdx.x, tid = threadIdx.x;
+    extern __shared__ __align__(16) unsigned char dyn_smem[];
+    // [NCOL][NSAMP][kmax] each; tab_a: edges between lattice columns (t_start = node_t(c-1)); tab_b: edges from the
+    // DP origin (column 0, and source row 0)
+    Interval *tab_a = reinterpret_cast<Interval *>(dyn_smem);
+    Interval *tab_b = tab_a + NCOL * NSAMP * p.kmax;
+    __shared__ WarpRing rings[ST_WARPS];
+    __shared__ int n_act_sm;
+    const int frame = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const double *sc = scenes + (size_t)frame * p.scene_stride;
     const double v0 = sc[0];
     const int K = p.kmax;
-    if (tid < K) {
-        obs[tid].s_in = sc[2 + tid];
-        obs[tid].s_out = sc[2 + K + tid];
-        obs[tid].t_in = sc[2 + 2 * K + tid];
-        obs[tid].t_out = sc[2 + 3 * K + tid];
+    if (tid == 0) {                                    // present obstacles, order kept (NaN s_in = absent, :255)
+        int n = 0;
+        for (int j = 0; j < K; ++j)
+            if (!isnan(sc[2 + j])) {
+                obs[n].s_in = sc[2 + j];
+                obs[n].s_out = sc[2 + K + j];
+                obs[n].t_in = sc[2 + 2 * K + j];
+                obs[n].t_out = sc[2 + 3 * K + j];
+                ++n;
+            }
+        n_act_sm = n;
     }
     if (tid < NROW) s_of[tid] = node_s(tid);
     __syncthreads();
+    const int n_act = n_act_sm;
+    for (int q = tid; q < NCOL * NSAMP * n_act; q += ST_THREADS) {
+        const int j = q % n_act, i = (q / n_act) % NSAMP, c = q / (n_act * NSAMP);
+        const Obs o = obs[j];
+        const double t_en = node_t(c);
+        if (c >= 1) {
+            const double t_st = node_t(c - 1);
+            tab_a[(c * NSAMP + i) * K + j] = capsule_slice(o.s_in, o.t_in, o.s_out, o.t_out, t_st + (double)(i - 1) * ((t_en - t_st) / (NSAMP - 1)));
+        }
+        tab_b[(c * NSAMP + i) * K + j] = capsule_slice(o.s_in, o.t_in, o.s_out, o.t_out, 0.0 + (double)(i - 1) * ((t_en - 0.0) / (NSAMP - 1)));
+    }
+    __syncthreads();
     const double INF = __longlong_as_double(0x7ff0000000000000LL);
+    const EmpStParams &P = p.prm;
+    WarpRing &ring = rings[warp];
+
+    // CalcDpCost (:191-231) around the warp-cooperative obstacle term
+    auto edge = [&](bool valid, double s_st, double t_st, double sd_st, double s_en, double t_en, const Interval *tab) {
+        const double cur = (s_en - s_st) / (t_en - t_st);
+        const double acc = (cur - sd_st) / (t_en - t_st);
+        const double dv = cur - P.reference_speed;
+        const double c_ref = P.w_ref_speed * (dv * dv);
+        double c_acc;
+        if (4 > acc && acc > -6) c_acc = P.w_accel * (acc * acc);
+        else c_acc = (100000 * P.w_accel) * (acc * acc);
+        const double c_obs = warp_obs_cost(valid, s_st, t_st, s_en, t_en, tab, K, obs, n_act, ring, P.w_obs,
+                                           p.lnw_hi, p.lnw_lo, lane);
+        return (c_obs + c_acc) + c_ref;
+    };
 
     // column 0: edges from the DP origin (:125-131)
-    if (tid < NROW) {
-        const double c = edge_cost(0.0, 0.0, v0, s_of[tid], node_t(0), obs, K, p.prm);
-        cost_sm[0][tid] = c;
-        sdot_sm[0][tid] = s_of[tid] / node_t(0);
-        node_sm[0][tid] = 0;
-        if (cost_tab) cost_tab[((size_t)frame * NROW + tid) * NCOL] = c;
-        if (sdot_tab) sdot_tab[((size_t)frame * NROW + tid) * NCOL] = sdot_sm[0][tid];
-        if (node_tab) node_tab[((size_t)frame * NROW + tid) * NCOL] = 0;
-        if (tid == 0) top_cost[0] = c;
+    for (int base = warp * 32; base < NROW; base += ST_THREADS) {
+        const int r = base + lane;
+        const bool valid = r < NROW;
+        const double c = edge(valid, 0.0, 0.0, v0, s_of[valid ? r : 0], node_t(0), tab_b);
+        if (valid) {
+            cost_sm[0][r] = c;
+            sdot_sm[0][r] = s_of[r] / node_t(0);
+            node_sm[0][r] = 0;
+            if (cost_tab) cost_tab[((size_t)frame * NROW + r) * NCOL] = c;
+            if (sdot_tab) sdot_tab[((size_t)frame * NROW + r) * NCOL] = sdot_sm[0][r];
+            if (node_tab) node_tab[((size_t)frame * NROW + r) * NCOL] = 0;
+            if (r == 0) top_cost[0] = c;
+        }
     }
     __syncthreads();
 
     for (int c = 1; c < NCOL; ++c) {
         const int prev = (c - 1) & 1, cur = c & 1;
         const double t_en = node_t(c), t_prev = node_t(c - 1);
-        for (int e = tid; e < NROW * NROW; e += ST_THREADS) {
+        for (int e = tid; e < NROW * NROW; e += ST_THREADS) {       // NROW*NROW is a multiple of 32: full warps
             const int k = e / NROW, j = e - k * NROW;            // source row k, target row j
             double s_st, t_st, sd_st;
+            const Interval *tab;
             if (k == 0) {                                        // row_start == 0 quirk (:208-212)
-                s_st = 0.0; t_st = 0.0; sd_st = v0;
+                s_st = 0.0; t_st = 0.0; sd_st = v0; tab = tab_b + c * NSAMP * K;
             } else {
-                s_st = s_of[k]; t_st = t_prev; sd_st = sdot_sm[prev][k];
+                s_st = s_of[k]; t_st = t_prev; sd_st = sdot_sm[prev][k]; tab = tab_a + c * NSAMP * K;
             }
-            const double ec = edge_cost(s_st, t_st, sd_st, s_of[j], t_en, obs, K, p.prm);
+            const double ec = edge(true, s_st, t_st, sd_st, s_of[j], t_en, tab);
             cand[e] = ec + cost_sm[prev][k];                     // cost_temp + dp_st_cost[pre] (:145)
         }
         __syncthreads();
@@ -123,7 +299,13 @@ st_dp_kernel(const double *__restrict__ scenes, double *__restrict__ out, double
 
 cudaError_t launch_st_dp(const double *scenes, double *out, double *cost_tab, double *sdot_tab, int32_t *node_tab,
                          const StLaunch &p, cudaStream_t st) {
-    st_dp_kernel<<<p.batch, ST_THREADS, 0, st>>>(scenes, out, cost_tab, sdot_tab, node_tab, p);
+    StLaunch q = p;
+    const long double lw = logl((long double)p.prm.w_obs);          // ln w_obs as a double-double
+    q.lnw_hi = (double)lw;
+    q.lnw_lo = (double)(lw - (long double)q.lnw_hi);
+    const size_t smem = (size_t)2 * NCOL * NSAMP * (p.kmax > 0 ? p.kmax : 1) * sizeof(Interval);
+    cudaFuncSetAttribute(st_dp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    st_dp_kernel<<<p.batch, ST_THREADS, smem, st>>>(scenes, out, cost_tab, sdot_tab, node_tab, q);
     return cudaGetLastError();
 }
 

@@ -10,6 +10,7 @@ constexpr int ST_THREADS = 128;
 struct StLaunch {
     EmpStParams prm;
     int batch, kmax, scene_stride;
+    double lnw_hi, lnw_lo;            // ln(w_obs), filled by launch_st_dp
 };
 
 cudaError_t launch_st_dp(const double *scenes, double *out, double *cost_tab, double *sdot_tab, int32_t *node_tab,
