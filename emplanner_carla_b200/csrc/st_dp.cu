@@ -21,9 +21,11 @@
 //   * per frame, for every (column, sample, obstacle) the s-interval in which a sample at that column's sample
 //     time can be within 1.6 of the segment is tabulated once (the sample times of a column are shared by all
 //     its edges) - the per-pair test is two comparisons;
-//   * the pairs that pass are compacted through a 64-slot ring per warp; whenever 32 are pending the warp
-//     evaluates them with all lanes busy (reference arithmetic, operands fetched from the owning lane by
-//     shuffle) and each owner adds its results in (sample, obstacle) order, so the sums stay bit-identical.
+//   * the pairs that pass are compacted into a per-warp queue (lane-major, positions from a warp scan of the
+//     per-lane counts); the warp evaluates them 32 at a time with all lanes busy (reference arithmetic,
+//     operands fetched from the owning lane by shuffle) and each owner adds its results in (sample, obstacle)
+//     order, so the sums stay bit-identical.
+#include <type_traits>
 #include "emp_common.cuh"
 #include "st_kernels.h"
 #include "st_device.cuh"
@@ -89,64 +91,73 @@ __device__ __forceinline__ double point_cost(double s, double t, const Obs o, do
     return 0.0;
 }
 
-struct WarpRing {
-    double val[64];
-    uint32_t desc[64];
+// Per-warp compaction queue: descriptors of every near (sample, obstacle) pair of the warp's 32 edges, lane-major,
+// and the 32 values of the batch in flight.
+struct WarpQueue {
+    uint16_t *desc;            // [32 * NSAMP * kmax]: owner lane | sample << 5 | obstacle << 8
+    double *val;               // [32]
 };
 
-// Obstacle cost (CalcObsCost :234-271) of one edge per lane, for a warp's 32 edges at once.
+// Obstacle cost (CalcObsCost :234-271) of one edge per lane, for a warp's 32 edges at once.  `tab` is warp-uniform.
+// HALF: every edge of the warp spans exactly one lattice column (t_en - t_st == 0.5): the divisions by 0.5 and
+// 0.125 become exact multiplications.
+template <bool HALF>
 __device__ __forceinline__ double warp_obs_cost(bool valid, double s_st, double t_st, double s_en, double t_en,
-                                                const Interval *tab /* [NSAMP][kmax] of this lane's edge kind */,
-                                                int kmax, const Obs *obs, int n_act, WarpRing &ring, double w_obs,
-                                                double lnw_hi, double lnw_lo, int lane) {
-    const double dt = (t_en - t_st) / (NSAMP - 1);
-    const double k = (s_en - s_st) / (t_en - t_st);
-    double cost = 0.0;
-    unsigned long long mine = 0ull;                        // ring slots holding this lane's pending pairs
-    int head = 0, count = 0;                               // warp-uniform
-    auto flush = [&](int n) {
-        __syncwarp();
-        const uint32_t d = ring.desc[(head + lane) & 63];
-        const bool have = lane < n;
-        const int ol = have ? (int)(d & 31u) : lane, i = (int)((d >> 5) & 7u), j = (int)(d >> 8);
-        const double os = shfl(s_st, ol), ot = shfl(t_st, ol), oe = shfl(s_en, ol);
-        if (have) {
-            const double odt = (t_en - ot) / (NSAMP - 1);
-            const double ok = (oe - os) / (t_en - ot);
-            const double t = ot + (double)(i - 1) * odt;               // sic: samples at (i-1)*dt (:251-252)
-            const double s = os + (ok * (double)(i - 1)) * odt;
-            ring.val[(head + lane) & 63] = point_cost(s, t, obs[j], w_obs, lnw_hi, lnw_lo);
-        }
-        __syncwarp();
-        unsigned long long m = ((mine >> head) | (head ? mine << (64 - head) : 0ull)) & ((n >= 64) ? ~0ull : ((1ull << n) - 1ull));
-        while (m) {                                        // own results, in (sample, obstacle) order
-            const int p = __ffsll((long long)m) - 1;
-            cost = cost + ring.val[(head + p) & 63];
-            mine &= ~(1ull << ((head + p) & 63));
-            m &= m - 1;
-        }
-        head = (head + n) & 63;
-        count -= n;
-    };
-#pragma unroll 1
+                                                const Interval *tab /* [NSAMP][kmax] */, int kmax, const Obs *obs,
+                                                int n_act, const WarpQueue &Q, double w_obs, double lnw_hi,
+                                                double lnw_lo, int lane) {
+    const double dt = HALF ? 0.125 : (t_en - t_st) / (NSAMP - 1);
+    const double k = HALF ? (s_en - s_st) * 2.0 : (s_en - s_st) / (t_en - t_st);
+    // 1. which pairs can cost anything: two comparisons against the column's interval table
+    uint32_t near[NSAMP];
+    int cnt = 0;
+#pragma unroll
     for (int i = 0; i < NSAMP; ++i) {
         const double s = s_st + (k * (double)(i - 1)) * dt;
+        uint32_t m = 0;
         for (int j = 0; j < n_act; ++j) {
             const Interval iv = tab[i * kmax + j];
-            const bool near = valid && iv.lo <= s && s <= iv.hi;
-            const unsigned b = __ballot_sync(EMP_FULL_MASK, near);
-            if (b) {
-                if (near) {
-                    const int pos = (head + count + __popc(b & ((1u << lane) - 1u))) & 63;
-                    ring.desc[pos] = (uint32_t)lane | ((uint32_t)i << 5) | ((uint32_t)j << 8);
-                    mine |= 1ull << pos;
-                }
-                count += __popc(b);
-                if (count >= 32) flush(32);
-            }
+            m |= (iv.lo <= s && s <= iv.hi ? 1u : 0u) << j;
         }
+        near[i] = valid ? m : 0u;
+        cnt += __popc(near[i]);
     }
-    if (count > 0) flush(count);
+    // 2. lane-major queue positions
+    int incl = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int v = __shfl_up_sync(EMP_FULL_MASK, incl, o);
+        if (lane >= o) incl += v;
+    }
+    const int total = __shfl_sync(EMP_FULL_MASK, incl, 31);
+    if (total == 0) return 0.0;
+    const int start = incl - cnt;
+    {
+        int pos = start;
+#pragma unroll
+        for (int i = 0; i < NSAMP; ++i)
+            for (uint32_t m = near[i]; m; m &= m - 1)
+                Q.desc[pos++] = (uint16_t)(lane | (i << 5) | ((__ffs(m) - 1) << 8));
+    }
+    // 3. evaluate 32 pairs at a time with all lanes busy; owners add their results in (sample, obstacle) order
+    double cost = 0.0;
+    for (int b0 = 0; b0 < total; b0 += 32) {
+        __syncwarp();
+        const bool have = b0 + lane < total;
+        const uint32_t d = have ? Q.desc[b0 + lane] : (uint32_t)lane;
+        const int ol = (int)(d & 31u), i = (int)((d >> 5) & 7u), j = (int)(d >> 8);
+        const double os = shfl(s_st, ol), ot = shfl(t_st, ol), oe = shfl(s_en, ol);
+        if (have) {
+            const double odt = HALF ? 0.125 : (t_en - ot) / (NSAMP - 1);
+            const double ok = HALF ? (oe - os) * 2.0 : (oe - os) / (t_en - ot);
+            const double t = ot + (double)(i - 1) * odt;               // sic: samples at (i-1)*dt (:251-252)
+            const double s = os + (ok * (double)(i - 1)) * odt;
+            Q.val[lane] = point_cost(s, t, obs[j], w_obs, lnw_hi, lnw_lo);
+        }
+        __syncwarp();
+        const int lo = max(start, b0), hi = min(start + cnt, b0 + 32);
+        for (int q = lo; q < hi; ++q) cost = cost + Q.val[q - b0];
+    }
     return cost;
 }
 
@@ -163,7 +174,8 @@ st_dp_kernel(const double *__restrict__ scenes, double *__restrict__ out, double
     // DP origin (column 0, and source row 0)
     Interval *tab_a = reinterpret_cast<Interval *>(dyn_smem);
     Interval *tab_b = tab_a + NCOL * NSAMP * p.kmax;
-    __shared__ WarpRing rings[ST_WARPS];
+    uint16_t *qdesc = reinterpret_cast<uint16_t *>(tab_b + NCOL * NSAMP * p.kmax);
+    __shared__ double qval[ST_WARPS][32];
     __shared__ int n_act_sm;
     const int frame = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const double *sc = scenes + (size_t)frame * p.scene_stride;
@@ -197,18 +209,20 @@ st_dp_kernel(const double *__restrict__ scenes, double *__restrict__ out, double
     __syncthreads();
     const double INF = __longlong_as_double(0x7ff0000000000000LL);
     const EmpStParams &P = p.prm;
-    WarpRing &ring = rings[warp];
+    const WarpQueue Q{qdesc + (size_t)warp * 32 * NSAMP * p.kmax, qval[warp]};
 
     // CalcDpCost (:191-231) around the warp-cooperative obstacle term
-    auto edge = [&](bool valid, double s_st, double t_st, double sd_st, double s_en, double t_en, const Interval *tab) {
-        const double cur = (s_en - s_st) / (t_en - t_st);
-        const double acc = (cur - sd_st) / (t_en - t_st);
+    auto edge = [&](auto half, bool valid, double s_st, double t_st, double sd_st, double s_en, double t_en,
+                    const Interval *tab) {
+        constexpr bool HALF = decltype(half)::value;
+        const double cur = HALF ? (s_en - s_st) * 2.0 : (s_en - s_st) / (t_en - t_st);
+        const double acc = HALF ? (cur - sd_st) * 2.0 : (cur - sd_st) / (t_en - t_st);
         const double dv = cur - P.reference_speed;
         const double c_ref = P.w_ref_speed * (dv * dv);
         double c_acc;
         if (4 > acc && acc > -6) c_acc = P.w_accel * (acc * acc);
         else c_acc = (100000 * P.w_accel) * (acc * acc);
-        const double c_obs = warp_obs_cost(valid, s_st, t_st, s_en, t_en, tab, K, obs, n_act, ring, P.w_obs,
+        const double c_obs = warp_obs_cost<HALF>(valid, s_st, t_st, s_en, t_en, tab, K, obs, n_act, Q, P.w_obs,
                                            p.lnw_hi, p.lnw_lo, lane);
         return (c_obs + c_acc) + c_ref;
     };
@@ -217,7 +231,7 @@ st_dp_kernel(const double *__restrict__ scenes, double *__restrict__ out, double
     for (int base = warp * 32; base < NROW; base += ST_THREADS) {
         const int r = base + lane;
         const bool valid = r < NROW;
-        const double c = edge(valid, 0.0, 0.0, v0, s_of[valid ? r : 0], node_t(0), tab_b);
+        const double c = edge(std::true_type{}, valid, 0.0, 0.0, v0, s_of[valid ? r : 0], node_t(0), tab_b);
         if (valid) {
             cost_sm[0][r] = c;
             sdot_sm[0][r] = s_of[r] / node_t(0);
@@ -233,17 +247,21 @@ st_dp_kernel(const double *__restrict__ scenes, double *__restrict__ out, double
     for (int c = 1; c < NCOL; ++c) {
         const int prev = (c - 1) & 1, cur = c & 1;
         const double t_en = node_t(c), t_prev = node_t(c - 1);
-        for (int e = tid; e < NROW * NROW; e += ST_THREADS) {       // NROW*NROW is a multiple of 32: full warps
-            const int k = e / NROW, j = e - k * NROW;            // source row k, target row j
-            double s_st, t_st, sd_st;
-            const Interval *tab;
-            if (k == 0) {                                        // row_start == 0 quirk (:208-212)
-                s_st = 0.0; t_st = 0.0; sd_st = v0; tab = tab_b + c * NSAMP * K;
-            } else {
-                s_st = s_of[k]; t_st = t_prev; sd_st = sdot_sm[prev][k]; tab = tab_a + c * NSAMP * K;
-            }
-            const double ec = edge(true, s_st, t_st, sd_st, s_of[j], t_en, tab);
-            cand[e] = ec + cost_sm[prev][k];                     // cost_temp + dp_st_cost[pre] (:145)
+        // edges from source rows k >= 1 (one interval table for the whole warp), then the 40 edges from source
+        // row 0, which the reference treats as starting at the DP origin (:208-212)
+        constexpr int NE1 = (NROW - 1) * NROW;
+        for (int base = warp * 32; base < NE1; base += ST_THREADS) {
+            const int e = NROW + base + lane;
+            const bool valid = base + lane < NE1;
+            const int k = valid ? e / NROW : 1, j = valid ? e - k * NROW : 0;
+            const double ec = edge(std::true_type{}, valid, s_of[k], t_prev, sdot_sm[prev][k], s_of[j], t_en, tab_a + c * NSAMP * K);
+            if (valid) cand[e] = ec + cost_sm[prev][k];          // cost_temp + dp_st_cost[pre] (:145)
+        }
+        for (int base = warp * 32; base < NROW; base += ST_THREADS) {
+            const int j = base + lane;
+            const bool valid = j < NROW;
+            const double ec = edge(std::false_type{}, valid, 0.0, 0.0, v0, s_of[valid ? j : 0], t_en, tab_b + c * NSAMP * K);
+            if (valid) cand[j] = ec + cost_sm[prev][0];
         }
         __syncthreads();
         if (tid < NROW) {
@@ -303,7 +321,8 @@ cudaError_t launch_st_dp(const double *scenes, double *out, double *cost_tab, do
     const long double lw = logl((long double)p.prm.w_obs);          // ln w_obs as a double-double
     q.lnw_hi = (double)lw;
     q.lnw_lo = (double)(lw - (long double)q.lnw_hi);
-    const size_t smem = (size_t)2 * NCOL * NSAMP * (p.kmax > 0 ? p.kmax : 1) * sizeof(Interval);
+    const size_t km = p.kmax > 0 ? p.kmax : 1;
+    const size_t smem = 2 * NCOL * NSAMP * km * sizeof(Interval) + (size_t)ST_WARPS * 32 * NSAMP * km * sizeof(uint16_t);
     cudaFuncSetAttribute(st_dp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     st_dp_kernel<<<p.batch, ST_THREADS, smem, st>>>(scenes, out, cost_tab, sdot_tab, node_tab, q);
     return cudaGetLastError();

@@ -5,7 +5,10 @@
 
 namespace emp {
 
-constexpr int ST_THREADS = 128;
+#ifndef EMP_ST_THREADS
+#define EMP_ST_THREADS 256
+#endif
+constexpr int ST_THREADS = EMP_ST_THREADS;
 
 struct StLaunch {
     EmpStParams prm;
