@@ -89,6 +89,8 @@ _SIGNATURES = {
     "emp_st_path_speed_merge_dev": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, _P, _P, _P]),
     "emp_st_back_host": (C.c_int, [_P, C.c_int, C.POINTER(SpeedQpParams), _P, _P, C.c_int, _P, C.c_int, _P, _P, _P, _P,
                                    _P, _P, C.c_int, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "emp_cycle_path_points_dev": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, _P, _P, _P]),
+    "emp_cycle_path_tables_dev": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, _P, _P, _P]),
     "emp_fp64_peak": (C.c_int, [C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "emp_planner_create": (C.c_int, [C.POINTER(_P), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),
     "emp_planner_destroy": (None, [_P]),

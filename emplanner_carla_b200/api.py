@@ -499,3 +499,55 @@ def fp64_peak(iters=4096):
     t, ms = C.c_double(), C.c_double()
     _lib.check(_lib.lib().emp_fp64_peak(int(iters), C.byref(t), C.byref(ms)))
     return t.value, ms.value
+
+
+class EmCycle:
+    """One full EM cycle for a batch on the current CUDA device (BASELINE.json configs[4]):
+        S-L DP -> [::2] -> corridor -> QP -> mid-point path (test_9.py:204-210) -> smooth_reference_line (QP#3)
+        + cal_heading_kappa -> trajectory_index2s -> S-T DP -> generate_convex_space -> speed QP
+        -> increase_points -> path_speed_merge.
+    Eleven launches on torch's current stream, no host round trip; torch tensors only hold the device buffers.
+    The batched cycle plans along the s-axis (no per-scene reference line among configs[4]'s inputs), for which
+    frenet_2_x_y_theta_kappa's projection is the identity."""
+
+    def __init__(self, batch, dp, qp, st, sq, sm, sl_kmax=8, st_kmax=8, device=None):
+        import torch
+        self.B, self.dp, self.qp, self.st, self.sq, self.sm = int(batch), dp, qp, st, sq, sm
+        self.sl_kmax, self.st_kmax = int(sl_kmax), int(st_kmax)
+        self.NE = max_enriched(dp)
+        self.MP = (self.NE + 1) // 2 + 1                  # mid-point path: n_qp + 1 points
+        if self.MP > 64:
+            raise ValueError("path of %d points exceeds the 64 points of the reference-line smoother" % self.MP)
+        self.NP = self.MP + 1                             # + NaN terminator (speed_planning_test.py:581)
+        dev = device if device is not None else torch.device("cuda", torch.cuda.current_device())
+        f64 = lambda *s: torch.zeros(s, dtype=torch.float64, device=dev)
+        i32 = lambda *s: torch.zeros(s, dtype=torch.int32, device=dev)
+        B = self.B
+        self.buf = dict(plans=f64(B, plan_stride(self.NE)), xy=f64(B, self.MP, 2), npts=i32(B), cart=f64(B, self.MP, 4),
+                        smooth_status_iters=i32(B, 2), path2=f64(B, 2, self.NP), path5=f64(B, 5, self.NP),
+                        st_out=f64(B, ST_OUT_STRIDE), bounds=f64(B, 4, ST_COLS), convex_status=i32(B),
+                        qp=f64(B, 4, ST_QP_POINTS), qp_status_iters=i32(B, 2), dense=f64(B, 4, ST_DENSE),
+                        dense_status=i32(B), traj=f64(B, 7, ST_DENSE), merge_status=i32(B))
+
+    def run(self, sl_scenes, st_scenes, start, current_time):
+        """sl_scenes [B, 6+2*sl_kmax], st_scenes [B, 2+4*st_kmax], start [B,2] = (s_dot, s_dot2), current_time [B]:
+        contiguous float64 CUDA tensors.  Enqueues the cycle and returns the buffer dict."""
+        L, sp, b, B, p = _lib.lib(), _stream_ptr(), self.buf, self.B, _dev_ptr
+        ck = _lib.check
+        ck(L.emp_sl_plan_dev(p(sl_scenes), self.sl_kmax, B, C.byref(self.dp), C.byref(self.qp), self.NE, p(b["plans"]),
+                             None, sp))
+        ck(L.emp_cycle_path_points_dev(p(b["plans"]), self.NE, B, self.MP, p(b["xy"]), p(b["npts"]), sp))
+        ck(L.emp_smooth_line_dev(p(b["xy"]), p(b["npts"]), self.MP, B, C.byref(self.sm), p(b["cart"]),
+                                 p(b["smooth_status_iters"]), sp))
+        ck(L.emp_cycle_path_tables_dev(p(b["cart"]), p(b["npts"]), self.MP, B, self.NP, p(b["path2"]), p(b["path5"]), sp))
+        ck(L.emp_st_dp_dev(p(st_scenes), self.st_kmax, B, C.byref(self.st), p(b["st_out"]), None, None, None, sp))
+        ck(L.emp_st_convex_space_dev(p(b["st_out"]), p(st_scenes), self.st_kmax, p(b["path2"]), self.NP, C.byref(self.sq),
+                                     B, p(b["bounds"]), p(b["convex_status"]), sp))
+        ck(L.emp_st_speed_qp_dev(p(start), p(b["st_out"]), p(b["bounds"]), B, C.byref(self.sq), p(b["qp"]),
+                                 p(b["qp_status_iters"]), sp))
+        ck(L.emp_st_increase_points_dev(p(b["qp"]), B, p(b["dense"]), p(b["dense_status"]), sp))
+        ck(L.emp_st_path_speed_merge_dev(p(b["dense"]), p(current_time), p(b["path5"]), self.NP, B, p(b["traj"]),
+                                         p(b["merge_status"]), sp))
+        return b
+
+    N_LAUNCHES = 10

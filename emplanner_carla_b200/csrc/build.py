@@ -16,7 +16,7 @@ ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-Xcompiler", "-ffp-contract=off",
           "--expt-relaxed-constexpr"]
 UNITS = [("sl_dp.cu", ["-fmad=false"]), ("sl_qp.cu", []), ("st_dp.cu", ["-fmad=false"]), ("frenet.cu", ["-fmad=false"]), ("smooth_qp.cu", []), ("misc.cu", ["-fmad=false"]), ("st_misc.cu", ["-fmad=false"]),
-         ("st_back.cu", ["-fmad=false"]), ("st_qp.cu", []),
+         ("st_back.cu", ["-fmad=false"]), ("st_qp.cu", []), ("cycle.cu", ["-fmad=false"]),
          ("fp64_peak.cu", []), ("capi.cu", [])]
 
 

@@ -13,6 +13,7 @@
 #include "misc_kernels.h"
 #include "st_misc_kernels.h"
 #include "st_back_kernels.h"
+#include "cycle_kernels.h"
 
 namespace {
 
@@ -764,6 +765,26 @@ int emp_misc_host(EmpPlanner *pl, int op, const double *in, int n, int batch, co
     }
     EMP_CK(cudaStreamSynchronize(pl->stream), "planner stream");
     return 0;
+}
+
+int emp_cycle_path_points_dev(const double *plans, int n_enr_max, int batch, int max_points, double *xy,
+                              int32_t *npts, void *stream) {
+    if (batch < 0 || n_enr_max < 2 || max_points < 3) return fail(-2, "bad batch / n_enr_max / max_points");
+    if (batch == 0) return 0;
+    if (!plans || !xy || !npts) return fail(-1, "NULL argument");
+    cudaError_t e = emp::launch_cycle_path_points(plans, emp_plan_stride(n_enr_max), n_enr_max, batch, max_points, xy,
+                                                  npts, (cudaStream_t)stream);
+    return e == cudaSuccess ? 0 : fail_cuda(e, "cycle_path_points launch");
+}
+
+int emp_cycle_path_tables_dev(const double *cart, const int32_t *npts, int max_points, int batch, int n_path,
+                              double *path2, double *path5, void *stream) {
+    if (batch < 0 || max_points < 1 || n_path < 2) return fail(-2, "bad batch / max_points / n_path");
+    if (batch == 0) return 0;
+    if (!cart || !npts || !path2 || !path5) return fail(-1, "NULL argument");
+    cudaError_t e = emp::launch_cycle_path_tables(cart, npts, max_points, batch, n_path, path2, path5,
+                                                  (cudaStream_t)stream);
+    return e == cudaSuccess ? 0 : fail_cuda(e, "cycle_path_tables launch");
 }
 
 int emp_st_convex_space_dev(const double *st_out, const double *scenes, int kmax, const double *path, int n_path,

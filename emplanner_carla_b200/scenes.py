@@ -85,6 +85,16 @@ def st_scenes(batch, config_id, k_fixed=KMAX):
                 v0=v0, nobs=nobs)
 
 
+def cycle_scenes(batch, lattice, config_id=4, st_k_fixed=None):
+    """Full EM cycle scenes (BASELINE.json configs[4]): config-3 S-L inputs + config-4 S-T inputs per frame,
+    plus the plan-start acceleration and the plan time stamp."""
+    sl = sl_scenes(batch, lattice, config_id)
+    st = st_scenes(batch, config_id, k_fixed=st_k_fixed)
+    a0 = _rng(config_id, 20).uniform(-1.0, 1.0, int(batch))
+    now = 0.1 * np.arange(int(batch), dtype=np.float64)
+    return dict(sl=sl, st=st, a0=a0, now=now)
+
+
 def reference_line(n_nodes=400, spacing=2.0, amp=8.0, wavelength=60.0):
     """Synthetic global route y = amp*sin(x/wavelength) as [(x, y), ...]."""
     xs = np.arange(n_nodes, dtype=np.float64) * spacing

@@ -268,6 +268,19 @@ int emp_st_back_host(EmpPlanner *pl, int batch, const EmpSpeedQpParams *p,
                      double *bounds, int32_t *convex_status, double *qp, int32_t *qp_status_iters,
                      double *dense, int32_t *dense_status, double *traj, int32_t *merge_status);
 
+/* ---- glue between the S-L and the S-T half of an EM cycle (K10) ---------------------------------
+ * In the reference this is list handling inside the driver scripts, not planner functions.
+ * emp_cycle_path_points_dev: test_9.py:204-210 - mid-point averaging of (dp_path_s[::2], qp_path_l) of every plan
+ *   record into the polyline handed to smooth_reference_line (QP#3), planned along the s-axis (x = s, y = l).
+ *   xy [batch, max_points, 2]; npts [batch] = n_qp + 1, or 0 when the frame has no QP path.
+ * emp_cycle_path_tables_dev: test_10.py:234-244 - (x, y, theta, kappa) rows cart [batch, max_points, 4] (output
+ *   of emp_smooth_line_dev) -> path2 [batch,2,n_path] = (trajectory_index2s, kappa) zero padded, and
+ *   path5 [batch,5,n_path] = (path_s, x, y, heading, kappa) NaN padded; n_path > max(npts). */
+int emp_cycle_path_points_dev(const double *plans, int n_enr_max, int batch, int max_points, double *xy,
+                              int32_t *npts, void *stream);
+int emp_cycle_path_tables_dev(const double *cart, const int32_t *npts, int max_points, int batch, int n_path,
+                              double *path2, double *path5, void *stream);
+
 /* ---- stand-alone pieces of the S-L DP (K6), host-buffer entry points ------------------------------
  * emp_quintic_host:   planning_utils.cal_quintic_coefficient (:671-703).  in [n,8] = (start_l, start_dl, start_ddl,
  *                     end_l, end_dl, end_ddl, start_s, end_s); out [n,6] coefficients of the absolute-s power basis.
