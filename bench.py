@@ -200,6 +200,9 @@ def main():
     ap.add_argument("--cpu-frames", type=int, default=1024, help="frames of the CPU baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-flush", action="store_true", help="do not flush L2 between timed steps")
+    ap.add_argument("--pipeline", type=int, default=2,
+                    help="batches in flight: step k+1's kernels (and copies) overlap step k's on another stream; "
+                         "1 = strictly serial steps")
     ap.add_argument("--gather", default="p2p", choices=["p2p", "nccl"],
                     help="N>1: p2p = plan records stored into peers' buffers by the QP kernel (CUDA IPC, NVLink); "
                          "nccl = one in-place NCCL all-gather after the kernels")
@@ -236,30 +239,35 @@ def main():
     scenes_d = torch.from_numpy(rec_host).to(dev)
     from emplanner_carla_b200 import sharding
     use_p2p = world > 1 and args.gather == "p2p"
-    gbuf = sharding.PeerGatherBuffer(B, stride, dev) if use_p2p else sharding.GatherBuffer(B, stride, dev)
+    P = max(1, min(args.pipeline, api.PLAN_SLOTS))
+    gbufs = [sharding.PeerGatherBuffer(B, stride, dev) if use_p2p else sharding.GatherBuffer(B, stride, dev)
+             for _ in range(P)]                                        # one gather buffer per batch in flight
+    gbuf = gbufs[0]
     mine = gbuf.mine                                                   # kernels write straight into the send slice
     flush = None if args.no_flush else torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     stream = torch.cuda.current_stream()
 
-    def step(ev=None):
+    def step(ev=None, gb=None, st=None):
+        gb = gb or gbuf
+        st = st or stream
         if ev:
-            ev[0].record(stream)
-        api.dp_device(scenes_d, dp, NE, plans=mine)
+            ev[0].record(st)
+        api.dp_device(scenes_d, dp, NE, plans=gb.mine)
         if ev:
-            ev[1].record(stream)
+            ev[1].record(st)
         if use_p2p:
-            api.plan_device_p2p_qp(scenes_d, qp, NE, mine, gbuf.peer_array, gbuf.n_peers)   # QP + peer stores
+            api.plan_device_p2p_qp(scenes_d, qp, NE, gb.mine, gb.peer_array, gb.n_peers)   # QP + peer stores
         else:
-            api.qp_device(scenes_d, qp, NE, mine)
+            api.qp_device(scenes_d, qp, NE, gb.mine)
         if ev:
-            ev[2].record(stream)
+            ev[2].record(st)
         if world > 1:
             if use_p2p:
-                gbuf.fence()                                           # 1-element all-reduce = cross-rank barrier
+                gb.fence()                                             # 1-element all-reduce = cross-rank barrier
             else:
-                gbuf.all_gather()                                      # one in-place NCCL all-gather of plan records
+                gb.all_gather()                                        # one in-place NCCL all-gather of plan records
         if ev:
-            ev[3].record(stream)
+            ev[3].record(st)
 
     for _ in range(args.warmup):
         step()
@@ -283,26 +291,75 @@ def main():
 
     t_dp = sum(e[0].elapsed_time(e[1]) for e in evs)
     t_qp = sum(e[1].elapsed_time(e[2]) for e in evs)
-    t_all = sum(e[0].elapsed_time(e[3]) for e in evs)                  # ms over the K timed steps
-    tt = torch.tensor([t_all, t_dp, t_qp], dtype=torch.float64, device=dev)
+    t_ser = sum(e[0].elapsed_time(e[3]) for e in evs)                  # ms over the K serial steps
+
+    # ---- the timed region of `value`: exactly K steps, P batches in flight ------------------
+    # Step k runs on stream k % P with its own plan/gather buffer, so step k+1's DP kernel overlaps step k's QP
+    # kernel (each kernel alone leaves the SMs half idle in its tail: profiles/).  One start and one end event on
+    # the launching stream bracket the region; the L2 flush stays inside it.
+    t_pipe = t_ser
+    if P > 1:
+        streams = [torch.cuda.Stream(device=dev) for _ in range(P)]
+        for k in range(P):
+            with torch.cuda.stream(streams[k]):
+                step(gb=gbufs[k], st=streams[k])
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        sampler2 = ClockSampler(local)
+        sampler2.start()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for st_ in streams:
+            st_.wait_event(e0)
+        for k in range(args.steps):
+            st_ = streams[k % P]
+            with torch.cuda.stream(st_):
+                if flush is not None:
+                    flush.fill_(k & 0xFF)
+                step(gb=gbufs[k % P], st=st_)
+        for st_ in streams:
+            stream.wait_stream(st_)
+        e1.record(stream)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        clocks = sampler2.stop()
+        t_pipe = e0.elapsed_time(e1)
+    tt = torch.tensor([t_pipe, t_dp, t_qp, t_ser], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-    t_all, t_dp, t_qp = [float(v) for v in tt.tolist()]
+    t_all, t_dp, t_qp, t_ser = [float(v) for v in tt.tolist()]
     value = B * world * args.steps / (t_all * 1e-3)
+    value_serial = B * world * args.steps / (t_ser * 1e-3)
 
     # ---- end-to-end through the host-buffer C ABI (what a drop-in caller gets) --------------
     planner = api.HostPlanner(max_batch=B, kmax=8, n_enr_max=NE, max_col=lat.col, device=local)
-    out = api.pinned_empty((B, stride))                              # page-locked host buffers, like a real ingest path
-    rec_pin = api.pinned_empty(rec_host.shape)
-    rec_pin[:] = rec_host
-    rec_host = rec_pin
-    for _ in range(args.warmup):
-        planner.plan(rec_host, dp, qp, out=out)
+    outs = [api.pinned_empty((B, stride)) for _ in range(P)]         # page-locked host buffers, like a real ingest path
+    recs = [api.pinned_empty(rec_host.shape) for _ in range(P)]
+    for r in recs:
+        r[:] = rec_host
+    rec_host, out = recs[0], outs[0]
+
+    def e2e_steps(n):
+        if P == 1:
+            for _ in range(n):
+                planner.plan(rec_host, dp, qp, out=out)
+            return
+        for k in range(n):                                             # every step: H2D of its scenes, D2H of its plans
+            if k >= P:
+                planner.plan_wait(k % P)
+            planner.plan_submit(k % P, recs[k % P], dp, qp, outs[k % P])
+        for k in range(P):
+            planner.plan_wait(k)
+
+    e2e_steps(args.warmup)
     if world > 1:
         dist.barrier()
     t0 = time.perf_counter()
-    for _ in range(args.steps):
-        planner.plan(rec_host, dp, qp, out=out)
+    e2e_steps(args.steps)
     e2e_s = time.perf_counter() - t0
     e2e_t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
     if world > 1:
@@ -342,7 +399,7 @@ def main():
     # quintics, a banded instead of dense KKT solve).  The roofline fraction that bounds the kernels is the FP64
     # pipe utilisation measured by ncu (profiles/, static per round), not this number.
     ref_flops = (dp_flops(lat, float(shard["nobs"].mean())) + 25e6) * B      # DP + dense-cvxopt QP (~25 MFLOP, §8(d))
-    ref_equiv = ref_flops / ((t_dp + t_qp) / args.steps * 1e-3) / 1e12
+    ref_equiv = ref_flops / (t_all / args.steps * 1e-3) / 1e12
     ncu = NCU_STATIC.get(lat.name, {})
 
     cpu = None
@@ -356,7 +413,10 @@ def main():
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": t_all / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "ms_per_step": t_all / args.steps, "higher_is_better": True,
+        "pipeline": {"batches_in_flight": P, "value_serial_steps": value_serial, "ms_per_serial_step": t_ser / args.steps,
+                     "note": "value: step k+1's DP kernel overlaps step k's QP kernel (stream k % P, own plan buffer); "
+                             "kernels_ms / roofline: the serial pass, one kernel at a time"}, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
         "config": {"workload": "batch=%d/GPU synthetic Frenet scenes, %dx%d S-L lattice (%s), 0-8 random obstacles, "
                                "DP->[::2]->corridor->QP%s" % (B, lat.col, lat.row, lat.name,
@@ -368,7 +428,7 @@ def main():
                    "l2": "flushed with a 256 MiB write between timed steps" if flush is not None else "not flushed",
                    "qp_optimal_fraction": frac_opt, "qp_mean_iterations": iters, "qp_iterations": it_stats},
         "kernels_ms": {"sl_dp_kernel": t_dp / args.steps, "sl_qp_kernel": t_qp / args.steps,
-                       "collective": max(t_all - t_dp - t_qp, 0.0) / args.steps},
+                       "collective": max(t_ser - t_dp - t_qp, 0.0) / args.steps},
         "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
                      "frac": achieved / hbm_peak, "traffic": ncu.get("dram_bytes_per_launch", {}).get(dom),
                      "peak_source": peak_src,
@@ -382,7 +442,8 @@ def main():
                     "note": "fraction of the FP64 roofline = ncu sm__pipe_fp64_cycles_active of the dominant kernel; "
                             "reference_equivalent counts the reference's operation count and may exceed the peak"},
         "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": int(rec_host.nbytes),
-                "d2h_bytes_per_step": int(out.nbytes), "api": "emp_sl_plan_host via HostPlanner.plan, page-locked host buffers"},
+                "d2h_bytes_per_step": int(out.nbytes), "api": ("emp_sl_plan_submit/emp_sl_plan_wait via HostPlanner.plan_submit, %d slots, " % P if P > 1 else
+                        "emp_sl_plan_host via HostPlanner.plan, ") + "page-locked host buffers"},
         "gpu_launches": 2 * args.steps, "collectives": (args.steps if world > 1 else 0),
         "clocks": clocks,
     }

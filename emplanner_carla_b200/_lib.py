@@ -95,6 +95,8 @@ _SIGNATURES = {
     "emp_planner_create": (C.c_int, [C.POINTER(_P), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),
     "emp_planner_destroy": (None, [_P]),
     "emp_sl_plan_host": (C.c_int, [_P, _P, C.c_int, _DPP, _QPP, _P, _P]),
+    "emp_sl_plan_submit": (C.c_int, [_P, C.c_int, _P, C.c_int, _DPP, _QPP, _P, _P]),
+    "emp_sl_plan_wait": (C.c_int, [_P, C.c_int]),
     "emp_sl_dp_host": (C.c_int, [_P, _P, C.c_int, _DPP, _P, _P]),
     "emp_qp_host": (C.c_int, [_P, _P, _P, _P, C.c_int, C.c_int, _QPP, _P, _P]),
     "emp_corridor_host": (C.c_int, [_P, _P, _P, C.c_int, _P, C.c_int, _QPP, _P, _P]),

@@ -16,6 +16,7 @@ from . import _lib
 from ._lib import EmpError, dp_params, qp_params, st_params, smooth_params, speed_qp_params  # noqa: F401  (re-exported)
 
 PLAN_HDR = 8
+PLAN_SLOTS = 4
 SCENE_HDR = 6
 
 DP_NO_OBSTACLE, DP_ALL_COLLIDE, DP_OVERFLOW = 1, 2, 4
@@ -192,6 +193,17 @@ class HostPlanner:
         _lib.check(_lib.lib().emp_sl_plan_host(self._h, _ptr(scenes), B, C.byref(dp), C.byref(qp), _ptr(plans),
                                                _ptr(rows) if want_rows else None))
         return PlanView(plans, self.n_enr_max), rows
+
+    def plan_submit(self, slot, scenes, dp, qp, out, rows=None):
+        """Pipelined plan(): enqueue one batch on `slot` (0..PLAN_SLOTS-1) and return at once; `scenes`, `out`
+        (and `rows`) must be page-locked arrays (pinned_empty) that stay alive until plan_wait(slot)."""
+        B = scenes.shape[0]
+        _lib.check(_lib.lib().emp_sl_plan_submit(self._h, int(slot), _ptr(scenes), B, C.byref(dp), C.byref(qp), _ptr(out),
+                                                 _ptr(rows) if rows is not None else None))
+
+    def plan_wait(self, slot):
+        """Block until the batch submitted on `slot` is in its host buffers."""
+        _lib.check(_lib.lib().emp_sl_plan_wait(self._h, int(slot)))
 
     def dp(self, scenes, dp, want_rows=True):
         """DP_algorithm for a batch (no QP)."""

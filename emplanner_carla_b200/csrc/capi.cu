@@ -67,6 +67,7 @@ int make_dp_launch(emp::DpLaunch &L, const EmpDpParams *p, int kmax, int batch, 
     L.off_f0 = off;    off += align_up(2 * EMP_NSAMPLE * 8, 16);       // f0[10] + um[10]
     L.off_nl = off;    off += EMP_MAX_ROW * 8;
     L.off_refc = off;  off += align_up(RR * 8, 16);
+    L.off_ltab = off;  off += align_up(EMP_NSAMPLE * RR * 8, 16);     // l of every (sample, edge): lattice constant
     L.off_warp = off;
     int w = 0;
     L.w_off_cand = w;   w += align_up(RR * 8, 16);
@@ -74,6 +75,8 @@ int make_dp_launch(emp::DpLaunch &L, const EmpDpParams *p, int kmax, int batch, 
     L.w_off_rows = w;   w += align_up(L.C * 4, 16);
     L.w_off_offs = w;   w += align_up((L.C + 1) * 4, 16);
     L.w_off_parent = w; w += align_up(L.C * L.R, 16);
+    L.w_off_sj = w;     w += align_up(L.C * 8, 16);
+    L.w_off_dlon = w;   w += align_up(EMP_NSAMPLE * 8, 16);
     L.warp_bytes = w;
     L.smem_bytes = (unsigned)(off + emp::DP_WARPS * w);
     if (L.smem_bytes > 227u * 1024u) return fail(-3, "lattice too large for shared memory (row*col)");
@@ -135,6 +138,13 @@ struct EmpPlanner {
     double *h_scenes = nullptr, *h_plans = nullptr;       // pinned staging
     int32_t *h_rows = nullptr;
     float last_ms = 0.f;
+    // pipelined planning (emp_sl_plan_submit / emp_sl_plan_wait): slot 0 reuses the buffers above
+    struct Slot {
+        cudaStream_t stream = nullptr;
+        double *d_scenes = nullptr, *d_plans = nullptr;
+        int32_t *d_rows = nullptr;
+        bool busy = false;
+    } slot[EMP_PLAN_SLOTS];
 };
 
 extern "C" {
@@ -405,6 +415,10 @@ void emp_planner_destroy(EmpPlanner *pl) {
     cudaFree(pl->d_scenes); cudaFree(pl->d_plans); cudaFree(pl->d_rows);
     cudaFree(pl->d_qp_in); cudaFree(pl->d_qp_out); cudaFree(pl->d_status);
     cudaFreeHost(pl->h_scenes); cudaFreeHost(pl->h_plans); cudaFreeHost(pl->h_rows);
+    for (int k = 0; k < EMP_PLAN_SLOTS; ++k) {
+        if (pl->slot[k].stream) { cudaStreamSynchronize(pl->slot[k].stream); cudaStreamDestroy(pl->slot[k].stream); }
+        if (k > 0) { cudaFree(pl->slot[k].d_scenes); cudaFree(pl->slot[k].d_plans); cudaFree(pl->slot[k].d_rows); }
+    }
     if (pl->ev0) cudaEventDestroy(pl->ev0);
     if (pl->ev1) cudaEventDestroy(pl->ev1);
     if (pl->stream) cudaStreamDestroy(pl->stream);
@@ -442,6 +456,53 @@ static int plan_host_impl(EmpPlanner *pl, const double *scenes, int batch, const
     if (!out_pinned) memcpy(plans, pl->h_plans, pb);
     if (rows && !rows_pinned) memcpy(rows, pl->h_rows, rb);
     cudaEventElapsedTime(&pl->last_ms, pl->ev0, pl->ev1);
+    return 0;
+}
+
+int emp_sl_plan_submit(EmpPlanner *pl, int slot, const double *scenes, int batch, const EmpDpParams *dp,
+                       const EmpQpParams *qp, double *plans, int32_t *rows) {
+    if (!pl || !scenes || !plans || !dp || !qp) return fail(-1, "NULL argument");
+    if (slot < 0 || slot >= EMP_PLAN_SLOTS) return fail(-2, "slot out of range");
+    if (batch < 1 || batch > pl->max_batch) return fail(-2, "batch exceeds planner capacity");
+    if (dp->col > pl->max_col) return fail(-2, "col exceeds planner capacity");
+    if (emp_max_enriched(dp) > pl->n_enr_max) return fail(-2, "lattice needs a larger n_enr_max than the planner was created with");
+    EmpPlanner::Slot &S = pl->slot[slot];
+    if (S.busy) return fail(-5, "slot still in flight: call emp_sl_plan_wait first");
+    if (!is_pinned(scenes) || !is_pinned(plans) || (rows && !is_pinned(rows)))
+        return fail(-2, "emp_sl_plan_submit needs page-locked host buffers (emp_host_alloc / cudaHostRegister)");
+    EMP_CK(cudaSetDevice(pl->device), "cudaSetDevice");
+    const size_t sb_max = (size_t)pl->max_batch * emp_scene_stride(pl->kmax) * 8;
+    const size_t pb_max = (size_t)pl->max_batch * emp_plan_stride(pl->n_enr_max) * 8;
+    if (!S.stream) {
+        EMP_CK(cudaStreamCreateWithFlags(&S.stream, cudaStreamNonBlocking), "slot stream");
+        if (slot == 0) {
+            S.d_scenes = pl->d_scenes; S.d_plans = pl->d_plans; S.d_rows = pl->d_rows;
+            EMP_CK(cudaStreamSynchronize(pl->stream), "planner stream");
+        } else {
+            EMP_CK(cudaMalloc(&S.d_scenes, sb_max), "slot scenes");
+            EMP_CK(cudaMalloc(&S.d_plans, pb_max), "slot plans");
+            EMP_CK(cudaMalloc(&S.d_rows, (size_t)pl->max_batch * pl->max_col * 4), "slot rows");
+        }
+    }
+    const size_t sb = (size_t)batch * emp_scene_stride(pl->kmax) * 8;
+    const size_t pb = (size_t)batch * emp_plan_stride(pl->n_enr_max) * 8;
+    EMP_CK(cudaMemcpyAsync(S.d_scenes, scenes, sb, cudaMemcpyHostToDevice, S.stream), "H2D scenes");
+    if (int rc = emp_sl_plan_dev(S.d_scenes, pl->kmax, batch, dp, qp, pl->n_enr_max, S.d_plans, rows ? S.d_rows : nullptr,
+                                 S.stream)) return rc;
+    EMP_CK(cudaMemcpyAsync(plans, S.d_plans, pb, cudaMemcpyDeviceToHost, S.stream), "D2H plans");
+    if (rows) EMP_CK(cudaMemcpyAsync(rows, S.d_rows, (size_t)batch * dp->col * 4, cudaMemcpyDeviceToHost, S.stream), "D2H rows");
+    S.busy = true;
+    return 0;
+}
+
+int emp_sl_plan_wait(EmpPlanner *pl, int slot) {
+    if (!pl) return fail(-1, "NULL argument");
+    if (slot < 0 || slot >= EMP_PLAN_SLOTS) return fail(-2, "slot out of range");
+    EmpPlanner::Slot &S = pl->slot[slot];
+    if (!S.busy) return 0;
+    EMP_CK(cudaSetDevice(pl->device), "cudaSetDevice");
+    EMP_CK(cudaStreamSynchronize(S.stream), "slot stream");
+    S.busy = false;
     return 0;
 }
 

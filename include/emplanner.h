@@ -35,6 +35,7 @@ extern "C" {
 #define EMP_MAX_KMAX 32          /* obstacle slots per scene record */
 #define EMP_MAX_QP_POINTS 32     /* QP stations per frame (one warp lane each) */
 #define EMP_MAX_PEERS 8          /* GPUs of one NVSwitch box */
+#define EMP_PLAN_SLOTS 4         /* batches in flight through emp_sl_plan_submit */
 #define EMP_ST_KMAX 16           /* dynamic-obstacle slots per S-T scene record */
 #define EMP_ST_ROWS 40           /* s samples of the S-T lattice, speed_planning_test.py:114 */
 #define EMP_ST_COLS 16           /* t samples (0.5 s), speed_planning_test.py:116 */
@@ -360,6 +361,13 @@ void emp_planner_destroy(EmpPlanner *pl);
  * D2H of plans (+ rows if not NULL); returns when the host buffers are valid. */
 int emp_sl_plan_host(EmpPlanner *pl, const double *scenes, int batch, const EmpDpParams *dp,
                      const EmpQpParams *qp, double *plans, int32_t *rows);
+/* Pipelined form of emp_sl_plan_host for a stream of batches: submit enqueues H2D -> DP -> QP -> D2H of one batch
+ * on slot `slot`'s own CUDA stream and returns at once; wait blocks until that slot's results are in `plans`
+ * (/`rows`).  Slots (0 .. EMP_PLAN_SLOTS-1) are independent, so the copies and kernels of consecutive batches
+ * overlap.  All host buffers must be page-locked and stay valid until the slot has been waited for. */
+int emp_sl_plan_submit(EmpPlanner *pl, int slot, const double *scenes, int batch, const EmpDpParams *dp,
+                       const EmpQpParams *qp, double *plans, int32_t *rows);
+int emp_sl_plan_wait(EmpPlanner *pl, int slot);
 int emp_sl_dp_host(EmpPlanner *pl, const double *scenes, int batch, const EmpDpParams *dp,
                    double *plans, int32_t *rows);
 int emp_qp_host(EmpPlanner *pl, const double *l_min, const double *l_max, const double *start_l_dl_ddl,

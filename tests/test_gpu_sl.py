@@ -153,3 +153,45 @@ def test_full_size_properties(planner):
     view3, _ = planner.plan(rec[perm], dp, qp)
     assert np.array_equal(view3.raw[:, :7], view.raw[perm][:, :7])
     assert np.array_equal(view3.qp_l, view.qp_l[perm])
+
+
+def test_pipelined_submit_wait_matches_synchronous_plan():
+    """emp_sl_plan_submit / emp_sl_plan_wait (batches in flight on their own streams) return exactly what the
+    synchronous emp_sl_plan_host returns, slot by slot; misuse is an argument error, not a crash."""
+    from emplanner_carla_b200 import api, scenes
+    lat = scenes.LATTICE_A
+    dp, qp = api.dp_params(**lat.kwargs()), api.qp_params()
+    NE = api.max_enriched(dp)
+    B = 96
+    pl = api.HostPlanner(max_batch=B, n_enr_max=NE, max_col=lat.col)
+    try:
+        batches = [api.pack_scenes(**scenes.sl_scenes(B, lat, 40 + k)) for k in range(6)]
+        want = [pl.plan(b, dp, qp)[0].raw.copy() for b in batches]
+        ins = [api.pinned_empty(batches[0].shape) for _ in range(api.PLAN_SLOTS)]
+        outs = [api.pinned_empty(want[0].shape) for _ in range(api.PLAN_SLOTS)]
+        got = [None] * len(batches)
+        for k, b in enumerate(batches):
+            s = k % api.PLAN_SLOTS
+            if k >= api.PLAN_SLOTS:
+                pl.plan_wait(s)
+                got[k - api.PLAN_SLOTS] = outs[s].copy()
+            ins[s][:] = b
+            pl.plan_submit(s, ins[s], dp, qp, outs[s])
+        for k in range(len(batches) - api.PLAN_SLOTS, len(batches)):
+            pl.plan_wait(k % api.PLAN_SLOTS)
+            got[k] = outs[k % api.PLAN_SLOTS].copy()
+        for k in range(len(batches)):
+            view_g, view_w = api.PlanView(got[k], NE), api.PlanView(want[k], NE)
+            assert np.array_equal(view_g.n_enr, view_w.n_enr) and np.array_equal(view_g.qp_status, view_w.qp_status)
+            for b in range(B):
+                n, m = int(view_w.n_enr[b]), int(view_w.n_qp[b])
+                assert np.array_equal(view_g.enr_l[b, :n], view_w.enr_l[b, :n])
+                assert np.array_equal(view_g.qp_l[b, :m], view_w.qp_l[b, :m])
+        pl.plan_submit(0, ins[0], dp, qp, outs[0])
+        with pytest.raises(api.EmpError):
+            pl.plan_submit(0, ins[0], dp, qp, outs[0])            # slot busy
+        pl.plan_wait(0)
+        with pytest.raises(api.EmpError):
+            pl.plan_submit(1, batches[0], dp, qp, outs[1])        # pageable input
+    finally:
+        pl.close()
