@@ -83,3 +83,36 @@ def test_kernel_arithmetic_model_matches_oracle_qp(tag):
             worst = max(worst, np.abs(x[:, 0] - g["qp_l"][b, :n]).max())
             n_checked += 1
     assert n_checked >= 8 and worst < 1e-8, worst
+
+
+def test_wire_format_round_trip_and_errors():
+    """Packed Pipe messages (reference test_9.py:390-392, :220): lossless round trip incl. empty lists and the
+    route-less form, the reference's tuple shape back out, truncation / wrong magic rejected."""
+    from emplanner_carla_b200 import wire
+    rng = np.random.default_rng(5)
+    route = rng.normal(size=(300, 4))
+    static = [(1.0, 2.0, 11.5), (3.5, -4.25, 30.0)]
+    dyn = [(9.0, 8.0, 20.0, 3.5)]
+    msg = wire.pack_request(static, dyn, (0.1, 0.2), (0.3, 0.4), (5.0, 0.5), (0.01, -0.02), route, [17], route_id=7)
+    assert len(msg) == 32 + 8 * (2 * 3 + 4 + 8 + 300 * 4) + 8
+    r = wire.unpack_request(msg)
+    assert r["route_id"] == 7 and np.array_equal(r["global_frenet_path"], route)
+    tup = wire.as_reference_tuple(r)
+    assert tup[0] == static and tup[1] == dyn and tup[2] == (0.1, 0.2) and tup[5] == (0.01, -0.02) and tup[7] == [17]
+    assert len(tup[6]) == 300 and tup[6][4] == tuple(route[4])
+    lean = wire.pack_request([], [], (0, 0), (1, 1), (2, 2), (3, 3), None, [], route_id=7)
+    assert len(lean) == 32 + 64
+    r2 = wire.unpack_request(lean)
+    assert r2["global_frenet_path"] is None and len(r2["static_obs_info"]) == 0
+    assert len(wire.as_reference_tuple(r2, route=route)[6]) == 300
+    with pytest.raises(wire.WireError):
+        wire.as_reference_tuple(r2)
+    with pytest.raises(wire.WireError):
+        wire.unpack_request(msg[:-16])
+    with pytest.raises(wire.WireError):
+        wire.unpack_reply(msg)
+    path = rng.normal(size=(23, 4))
+    rep = wire.unpack_reply(wire.pack_reply(path, [17, 3], np.arange(26.0), -np.arange(26.0)))
+    assert np.array_equal(rep["path"], path) and list(rep["match_point_list"]) == [17, 3] and rep["path_l"][5] == -5.0
+    xy, n = wire.stack_obstacles([r, r2], kmax=4)
+    assert xy.shape == (2, 4, 2) and list(n) == [2, 0] and xy[0, 1, 1] == -4.25 and np.isnan(xy[1]).all()
