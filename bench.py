@@ -37,10 +37,10 @@ SCENE_BYTES = 164
 # Static ncu facts of the current kernels (one `ncu --set full` capture per change, see profiles/): the FP64 pipe
 # utilisation is the compute-roofline fraction; dram bytes per launch (batch 4096) go into roofline.traffic.
 NCU_STATIC = {
-    "C_60x11": {"fp64_pipe_active": {"sl_dp_kernel": 0.353, "sl_qp_kernel": 0.290},
-                "issue_active": {"sl_dp_kernel": 0.472, "sl_qp_kernel": 0.423},
-                "dram_bytes_per_launch": {"sl_dp_kernel": 842240 + 477952, "sl_qp_kernel": 5516800},
-                "source": "profiles/r1_ncu_full_v4_summary.txt (batch 4096, lattice C)"},
+    "C_60x11": {"fp64_pipe_active": {"sl_dp_kernel": 0.317, "sl_qp_kernel": 0.379},
+                "issue_active": {"sl_dp_kernel": 0.612, "sl_qp_kernel": 0.433},
+                "dram_bytes_per_launch": {"sl_dp_kernel": 1386752 + 218368, "sl_qp_kernel": 5506048},
+                "source": "profiles/r1_ncu_sl_final_summary.txt (batch 4096, lattice C, serial pass)"},
 }
 
 
