@@ -3,13 +3,17 @@
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--batch B] [--lattice C]
 
-One "step" = one pass of the hot path (DP kernel -> corridor+QP kernel [-> NCCL all-gather when
+One "step" = one pass of the hot path (DP kernel -> corridor+QP kernel [-> gather of the plan records when
 N > 1]) over one batch of synthetic Frenet scenes.  Default workload = BASELINE.json configs[1]:
 batch 4096 per GPU, 60x11 S-L lattice, 0-8 random obstacles (weak scaling: per-GPU batch fixed).
 
-  value     frames/s, inputs resident in HBM, CUDA events on the launching stream, max over ranks
-  e2e       frames/s through the host-buffer C ABI call (emp_sl_plan_host): host numpy buffers in,
-            host buffers out, H2D + D2H inside the timed region
+  value     frames/s over exactly K steps, inputs resident in HBM, one start and one end CUDA event on the
+            launching stream, max over ranks; --pipeline P (default 2) batches are in flight: step k runs on
+            stream k % P with its own plan/gather buffer, so step k+1's DP kernel overlaps step k's QP kernel
+  pipeline  the same K steps strictly one after the other (value_serial_steps); kernels_ms and roofline come
+            from this serial pass (events around each kernel)
+  e2e       frames/s through the host-buffer C ABI (emp_sl_plan_submit / emp_sl_plan_wait, P slots; emp_sl_plan_host
+            for P = 1): page-locked host buffers in and out, H2D + D2H of every step inside the timed region
   roofline  dominant kernel's algorithmic HBM bytes / its CUDA-event duration vs MEASURED_PEAKS hbm_gbs
   compute   same launch against the FP64 FMA peak measured on this GPU (the binding roofline)
   cpu_baseline  the oracle port (numpy float64, oracle/) on a bounded prefix of the same batch, all cores
@@ -62,7 +66,7 @@ def qp_flops(n, iters_mean):
 class ClockSampler(threading.Thread):
     """Samples SM clock + throttle reasons during the timed region (B200_PROFILING.md clocks line)."""
 
-    def __init__(self, index=0, period=0.01):
+    def __init__(self, index=0, period=0.002):
         super().__init__(daemon=True)
         self.index, self.period = index, period
         self.samples, self.reasons = [], set()

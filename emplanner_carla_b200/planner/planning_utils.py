@@ -177,3 +177,24 @@ def Frenet2Cartesian(s_set, l_set, dl_set, ddl_set, frenet_path_x, frenet_path_y
     for c in range(4):
         out[c][:n, 0] = o[c]
     return tuple(out)
+
+
+def cal_proj_point_1(s, pre_match_index, frenet_path_opt: list, s_map: list):
+    """Projection of arc length s on the reference line (reference :647-668; the same walk as
+    path_planning.cal_proj_point).  Returns (proj_x, proj_y, proj_theta, proj_kappa, match_index)."""
+    from . import path_planning
+    return path_planning.cal_proj_point(s, pre_match_index, frenet_path_opt, s_map)
+
+
+def predict_block_based_on_frenet(vehicle_loc, vehicle_velocity, local_frenet_path_opt, cur_path_s, cur_path_l, ts=0.1):
+    """Ego position one planning period ahead, along the current path (reference :617-644).  vehicle_loc /
+    vehicle_velocity only need .x/.y(/.z) attributes (carla.Location / carla.Vector3D in the reference)."""
+    import math
+    speed = math.sqrt(vehicle_velocity.x * vehicle_velocity.x + vehicle_velocity.y * vehicle_velocity.y +
+                      vehicle_velocity.z * vehicle_velocity.z)
+    s_map = cal_s_map_fun(local_frenet_path_opt, origin_xy=(vehicle_loc.x, vehicle_loc.y))
+    s = max(cur_path_s[0], 0) + speed * ts
+    index = int(np.argmin(abs(np.array(cur_path_s) - s)))          # nearest sample of the current path: a selection
+    l = cur_path_l[index]
+    proj_x, proj_y, proj_theta, _, _ = cal_proj_point_1(s, 0, local_frenet_path_opt, s_map)
+    return proj_x + l * -math.sin(proj_theta), proj_y + l * math.cos(proj_theta)

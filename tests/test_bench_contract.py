@@ -1,0 +1,43 @@
+"""bench.py's JSON contract: the reference arm runs anywhere (CPU oracle port); the product arm needs a GPU."""
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+
+from conftest import ROOT
+
+BASE_KEYS = {"metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+             "vs_baseline", "dtype", "data", "config", "e2e", "gpu_launches"}
+
+
+def _run(args, timeout=600):
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py")] + args, capture_output=True, text=True,
+                         timeout=timeout, cwd=ROOT)
+    assert out.returncode == 0, out.stderr[-2000:]
+    return json.loads(out.stdout.strip().splitlines()[-1])
+
+
+def test_reference_arm_line_on_cpu():
+    d = _run(["--impl", "reference", "--steps", "1", "--warmup", "0", "--cpu-frames", "16", "--lattice", "A"])
+    assert d["impl"] == "reference" and BASE_KEYS <= set(d)
+    assert d["metric"].startswith("planning frames/sec") and d["unit"] == "frames/s" and d["value"] > 0
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    assert d["e2e"] == {"value": d["value"], "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert d["vs_baseline"] is None and d["dtype"] == "f64" and "workload" in d["config"]
+
+
+@pytest.mark.gpu
+def test_product_arm_line_on_gpu():
+    d = _run(["--steps", "3", "--warmup", "3", "--cpu-frames", "32", "--batch", "512"])
+    assert BASE_KEYS <= set(d) and "impl" not in d
+    assert d["n_gpus"] == 1 and d["steps"] == 3 and d["higher_is_better"] is True and d["scaling"] == "weak"
+    r = d["roofline"]
+    assert r["bound"] == "hbm" and r["unit"] == "GB/s" and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-12
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["value"] > 0 and d["cpu_baseline"]["sample"]
+    e = d["e2e"]
+    assert e["value"] > 0 and e["h2d_bytes_per_step"] == 512 * 22 * 8 and e["d2h_bytes_per_step"] == 512 * 224 * 8
+    assert d["gpu_launches"] == 6 and d["value"] > d["cpu_baseline"]["value"]
+    assert set(d["clocks"]) >= {"sm_mhz", "sm_max_mhz", "reasons"}
+    assert d["pipeline"]["batches_in_flight"] >= 1 and d["pipeline"]["value_serial_steps"] > 0

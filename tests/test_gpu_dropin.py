@@ -138,3 +138,28 @@ def test_standalone_dp_pieces(planner_pkg):
     want = ofr.projection_s(line, mi, pts, smap)
     got = pu.cal_projection_s_fun(line, mi, pts, smap)
     assert np.abs(np.array(got) - np.array(want)).max() < 1e-9
+
+
+def test_predict_block_based_on_frenet_and_cal_proj_point_1(planner_pkg):
+    """planning_utils.predict_block_based_on_frenet (:617) / cal_proj_point_1 (:647) against the oracle's proj_point
+    on a golden reference line; tolerance 1e-9."""
+    import types
+    from oracle import frenet as ofr
+    from planner import planning_utils
+    g = load_golden("frenet.npz")
+    f = 3
+    line = [tuple(r) for r in g["line"][f]]
+    ego = g["ego"][f]
+    loc = types.SimpleNamespace(x=float(ego[0]), y=float(ego[1]))
+    vel = types.SimpleNamespace(x=6.0, y=1.5, z=0.0)
+    cur_s = list(np.arange(0.0, 40.0, 2.0))
+    cur_l = list(0.3 * np.sin(np.arange(20) / 3.0))
+    got = planning_utils.predict_block_based_on_frenet(loc, vel, line, cur_s, cur_l, ts=0.2)
+    smap = ofr.s_map(line, (loc.x, loc.y))
+    s = max(cur_s[0], 0) + np.hypot(6.0, 1.5) * 0.2
+    l = cur_l[int(np.argmin(abs(np.array(cur_s) - s)))]
+    px, py, pth, _, idx = ofr.proj_point(s, 0, line, smap)
+    want = (px - l * np.sin(pth), py + l * np.cos(pth))
+    assert np.allclose(got, want, rtol=0, atol=1e-9)
+    r1 = planning_utils.cal_proj_point_1(s, 0, line, smap)
+    assert np.allclose(r1[:4], ofr.proj_point(s, 0, line, smap)[:4], rtol=0, atol=1e-9) and r1[4] == idx
