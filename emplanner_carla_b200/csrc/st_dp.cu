@@ -34,6 +34,14 @@ namespace emp {
 namespace {
 
 constexpr int ST_WARPS = ST_THREADS / 32;
+#ifndef EMP_ST_PRUNE_M
+#define EMP_ST_PRUNE_M 1
+#endif
+#ifndef EMP_ST_PRUNE_ROUNDS
+#define EMP_ST_PRUNE_ROUNDS 3
+#endif
+constexpr int PRUNE_M = EMP_ST_PRUNE_M;            // candidates per target row evaluated per bounding round
+constexpr int PRUNE_ROUNDS = EMP_ST_PRUNE_ROUNDS;  // bounding rounds (the last one takes every candidate left under the bound)
 constexpr double NEAR_R = 1.6;        // > 1.5: beyond it CalcCollisionCost returns exactly 0 (margin covers rounding)
 
 struct Interval { double lo, hi; };
@@ -104,8 +112,8 @@ struct WarpQueue {
 template <bool HALF>
 __device__ __forceinline__ double warp_obs_cost(bool valid, double s_st, double t_st, double s_en, double t_en,
                                                 const Interval *tab /* [NSAMP][kmax] */, int kmax, const Obs *obs,
-                                                int n_act, const WarpQueue &Q, double w_obs, double lnw_hi,
-                                                double lnw_lo, int lane) {
+                                                uint32_t col_obs /* obstacles with a non-empty interval in this column */,
+                                                const WarpQueue &Q, double w_obs, double lnw_hi, double lnw_lo, int lane) {
     const double dt = HALF ? 0.125 : (t_en - t_st) / (NSAMP - 1);
     const double k = HALF ? (s_en - s_st) * 2.0 : (s_en - s_st) / (t_en - t_st);
     // 1. which pairs can cost anything: two comparisons against the column's interval table
@@ -115,7 +123,8 @@ __device__ __forceinline__ double warp_obs_cost(bool valid, double s_st, double 
     for (int i = 0; i < NSAMP; ++i) {
         const double s = s_st + (k * (double)(i - 1)) * dt;
         uint32_t m = 0;
-        for (int j = 0; j < n_act; ++j) {
+        for (uint32_t rest = col_obs; rest; rest &= rest - 1) {
+            const int j = __ffs(rest) - 1;
             const Interval iv = tab[i * kmax + j];
             m |= (iv.lo <= s && s <= iv.hi ? 1u : 0u) << j;
         }
@@ -161,7 +170,10 @@ __device__ __forceinline__ double warp_obs_cost(bool valid, double s_st, double 
     return cost;
 }
 
-__global__ void __launch_bounds__(ST_THREADS)
+#ifndef EMP_ST_MINBLOCKS
+#define EMP_ST_MINBLOCKS 3
+#endif
+__global__ void __launch_bounds__(ST_THREADS, EMP_ST_MINBLOCKS)
 st_dp_kernel(const double *__restrict__ scenes, double *__restrict__ out, double *__restrict__ cost_tab,
              double *__restrict__ sdot_tab, int32_t *__restrict__ node_tab, const StLaunch p) {
     __shared__ double cand[NROW * NROW];              // [k][j]: source-major, conflict-free both ways
@@ -176,6 +188,11 @@ st_dp_kernel(const double *__restrict__ scenes, double *__restrict__ out, double
     Interval *tab_b = tab_a + NCOL * NSAMP * p.kmax;
     uint16_t *qdesc = reinterpret_cast<uint16_t *>(tab_b + NCOL * NSAMP * p.kmax);
     __shared__ double qval[ST_WARPS][32];
+    __shared__ double ub_sm[NROW];
+    __shared__ unsigned short elist[NROW * NROW];      // edges to evaluate exactly in this column
+    __shared__ unsigned char estate[NROW * NROW];      // 1: already listed
+    __shared__ int n_list;
+    __shared__ uint32_t col_obs_a[NCOL], col_obs_b[NCOL];  // per column: obstacles any sample of the column can be near
     __shared__ int n_act_sm;
     const int frame = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const double *sc = scenes + (size_t)frame * p.scene_stride;
@@ -207,13 +224,25 @@ st_dp_kernel(const double *__restrict__ scenes, double *__restrict__ out, double
         tab_b[(c * NSAMP + i) * K + j] = capsule_slice(o.s_in, o.t_in, o.s_out, o.t_out, 0.0 + (double)(i - 1) * ((t_en - 0.0) / (NSAMP - 1)));
     }
     __syncthreads();
+    if (tid < 2 * NCOL) {
+        const int c = tid >> 1;
+        const Interval *t = ((tid & 1) ? tab_b : tab_a) + c * NSAMP * K;
+        uint32_t m = 0;
+        if ((tid & 1) || c >= 1)
+            for (int i = 0; i < NSAMP; ++i)
+                for (int j = 0; j < n_act; ++j)
+                    if (t[i * K + j].lo <= t[i * K + j].hi) m |= 1u << j;
+        ((tid & 1) ? col_obs_b : col_obs_a)[c] = m;
+    }
+    __syncthreads();
     const double INF = __longlong_as_double(0x7ff0000000000000LL);
     const EmpStParams &P = p.prm;
+    const bool prune = P.w_obs >= 0.0;                 // the bound needs a non-negative obstacle term
     const WarpQueue Q{qdesc + (size_t)warp * 32 * NSAMP * p.kmax, qval[warp]};
 
     // CalcDpCost (:191-231) around the warp-cooperative obstacle term
     auto edge = [&](auto half, bool valid, double s_st, double t_st, double sd_st, double s_en, double t_en,
-                    const Interval *tab) {
+                    const Interval *tab, uint32_t col_obs) {
         constexpr bool HALF = decltype(half)::value;
         const double cur = HALF ? (s_en - s_st) * 2.0 : (s_en - s_st) / (t_en - t_st);
         const double acc = HALF ? (cur - sd_st) * 2.0 : (cur - sd_st) / (t_en - t_st);
@@ -222,7 +251,7 @@ st_dp_kernel(const double *__restrict__ scenes, double *__restrict__ out, double
         double c_acc;
         if (4 > acc && acc > -6) c_acc = P.w_accel * (acc * acc);
         else c_acc = (100000 * P.w_accel) * (acc * acc);
-        const double c_obs = warp_obs_cost<HALF>(valid, s_st, t_st, s_en, t_en, tab, K, obs, n_act, Q, P.w_obs,
+        const double c_obs = warp_obs_cost<HALF>(valid, s_st, t_st, s_en, t_en, tab, K, obs, col_obs, Q, P.w_obs,
                                            p.lnw_hi, p.lnw_lo, lane);
         return (c_obs + c_acc) + c_ref;
     };
@@ -231,7 +260,7 @@ st_dp_kernel(const double *__restrict__ scenes, double *__restrict__ out, double
     for (int base = warp * 32; base < NROW; base += ST_THREADS) {
         const int r = base + lane;
         const bool valid = r < NROW;
-        const double c = edge(std::true_type{}, valid, 0.0, 0.0, v0, s_of[valid ? r : 0], node_t(0), tab_b);
+        const double c = edge(std::true_type{}, valid, 0.0, 0.0, v0, s_of[valid ? r : 0], node_t(0), tab_b, col_obs_b[0]);
         if (valid) {
             cost_sm[0][r] = c;
             sdot_sm[0][r] = s_of[r] / node_t(0);
@@ -247,23 +276,93 @@ st_dp_kernel(const double *__restrict__ scenes, double *__restrict__ out, double
     for (int c = 1; c < NCOL; ++c) {
         const int prev = (c - 1) & 1, cur = c & 1;
         const double t_en = node_t(c), t_prev = node_t(c - 1);
-        // edges from source rows k >= 1 (one interval table for the whole warp), then the 40 edges from source
-        // row 0, which the reference treats as starting at the DP origin (:208-212)
+        // ---- exact branch and bound over the 40 x 40 candidates of the column --------------------------------
+        // The obstacle term is >= 0 and rounding is monotone, so a candidate's value without it,
+        //   lb = (c_acc + c_ref) + dp_st_cost[k],   is a lower bound of   ((c_obs + c_acc) + c_ref) + dp_st_cost[k].
+        // Per target row and round: the PRUNE_M not yet evaluated candidates with the smallest lb (<= ub) are
+        // evaluated exactly; the best exact value so far, ub, bounds the row's result from above; the last round
+        // evaluates every candidate left with lb <= ub; the rest (lb > ub) cannot be the minimum nor tie with it,
+        // and keep lb in `cand`.  The (cost, k) arg-min below therefore sees
+        // the same winner, bit for bit, as the reference's full sweep (:134-152) - for ~1/5 of the obstacle work.
         constexpr int NE1 = (NROW - 1) * NROW;
-        for (int base = warp * 32; base < NE1; base += ST_THREADS) {
-            const int e = NROW + base + lane;
-            const bool valid = base + lane < NE1;
+        const Interval *ta = tab_a + c * NSAMP * K;
+        auto eval = [&](bool valid, int e) {                       // exact candidate value of edge e (k >= 1)
             const int k = valid ? e / NROW : 1, j = valid ? e - k * NROW : 0;
-            const double ec = edge(std::true_type{}, valid, s_of[k], t_prev, sdot_sm[prev][k], s_of[j], t_en, tab_a + c * NSAMP * K);
+            const double ec = edge(std::true_type{}, valid, s_of[k], t_prev, sdot_sm[prev][k], s_of[j], t_en, ta, col_obs_a[c]);
             if (valid) cand[e] = ec + cost_sm[prev][k];          // cost_temp + dp_st_cost[pre] (:145)
+        };
+        for (int e = NROW + tid; e < NROW * NROW; e += ST_THREADS) {
+            const int k = e / NROW, j = e - k * NROW;
+            const double cur_v = (s_of[j] - s_of[k]) * 2.0;        // t_en - t_prev == 0.5 exactly
+            const double acc = (cur_v - sdot_sm[prev][k]) * 2.0;
+            const double dv = cur_v - P.reference_speed;
+            const double c_ref = P.w_ref_speed * (dv * dv);
+            const double c_acc = (4 > acc && acc > -6) ? P.w_accel * (acc * acc) : (100000 * P.w_accel) * (acc * acc);
+            cand[e] = (c_acc + c_ref) + cost_sm[prev][k];
+            estate[e] = 0;
         }
-        for (int base = warp * 32; base < NROW; base += ST_THREADS) {
-            const int j = base + lane;
-            const bool valid = j < NROW;
-            const double ec = edge(std::false_type{}, valid, 0.0, 0.0, v0, s_of[valid ? j : 0], t_en, tab_b + c * NSAMP * K);
-            if (valid) cand[j] = ec + cost_sm[prev][0];
-        }
+        if (tid == 0) n_list = 0;
         __syncthreads();
+#pragma unroll 1
+        for (int round = 0, lo = 0; round < PRUNE_ROUNDS; ++round) {
+            const bool last = round == PRUNE_ROUNDS - 1;
+            if (!prune) {                                          // no bound available: every edge is listed
+                if (round == 0) {
+                    for (int e = NROW + tid; e < NROW * NROW; e += ST_THREADS) elist[e - NROW] = (unsigned short)e;
+                    if (tid == 0) n_list = NE1;
+                }
+            } else {
+                if (tid < NROW) {
+                    // upper bound of the row's result: the best exact value so far (source row 0 is exact after round 0)
+                    double ub = round == 0 ? INF : cand[tid];
+                    if (!(ub == ub)) ub = INF;
+                    if (round > 0)
+                        for (int k = 1; k < NROW; ++k) {
+                            const double v = cand[k * NROW + tid];
+                            if (estate[k * NROW + tid] && v < ub) ub = v;
+                        }
+                    ub_sm[tid] = ub;
+                    if (!last) {                                   // next: the PRUNE_M smallest lower bounds still <= ub
+                        for (int r = 0; r < PRUNE_M; ++r) {
+                            double best = INF;
+                            int kb = -1;
+                            for (int k = 1; k < NROW; ++k) {
+                                const double v = cand[k * NROW + tid];
+                                if (!estate[k * NROW + tid] && v < best) { best = v; kb = k; }
+                            }
+                            if (kb < 0 || !(best <= ub)) break;
+                            estate[kb * NROW + tid] = 1;
+                            elist[atomicAdd(&n_list, 1)] = (unsigned short)(kb * NROW + tid);
+                        }
+                    }
+                }
+                if (last) {                                        // finally: every candidate that can still win or tie
+                    __syncthreads();
+                    for (int e = NROW + tid; e < NROW * NROW; e += ST_THREADS)
+                        if (!estate[e] && cand[e] <= ub_sm[e % NROW]) elist[atomicAdd(&n_list, 1)] = (unsigned short)e;
+                }
+            }
+            __syncthreads();
+            const int hi = n_list;
+            const int n_grp = (hi - lo + 31) >> 5;                 // groups of 32 listed edges ...
+            const int n_all = n_grp + (round == 0 ? (NROW + 31) / 32 : 0);   // ... + in round 0 the source-row-0 edges
+            for (int g = warp; g < n_all; g += ST_WARPS) {
+                if (g < n_grp) {
+                    const int base = lo + 32 * g;
+                    const bool valid = base + lane < hi;
+                    eval(valid, valid ? elist[base + lane] : NROW);
+                } else {
+                    // the 40 edges from source row 0, which the reference treats as starting at the DP origin
+                    // (:208-212): always evaluated exactly
+                    const int j = 32 * (g - n_grp) + lane;
+                    const bool valid = j < NROW;
+                    const double ec = edge(std::false_type{}, valid, 0.0, 0.0, v0, s_of[valid ? j : 0], t_en, tab_b + c * NSAMP * K, col_obs_b[c]);
+                    if (valid) cand[j] = ec + cost_sm[prev][0];
+                }
+            }
+            lo = hi;
+            __syncthreads();
+        }
         if (tid < NROW) {
             double best = INF;                                    // dp_st_cost initialised to inf (:119)
             int kb = 0;
