@@ -76,7 +76,9 @@ int make_dp_launch(emp::DpLaunch &L, const EmpDpParams *p, int kmax, int batch, 
     L.w_off_offs = w;   w += align_up((L.C + 1) * 4, 16);
     L.w_off_parent = w; w += align_up(L.C * L.R, 16);
     L.w_off_sj = w;     w += align_up(L.C * 8, 16);
-    L.w_off_dlon = w;   w += align_up(EMP_NSAMPLE * 8, 16);
+    L.w_off_dlon = w;   w += align_up((kmax > 0 ? kmax : 1) * (EMP_NSAMPLE + 1) * 8, 16);
+    L.w_off_k0 = w;     w += EMP_MAX_ROW * 4;
+    L.w_off_wl = w;     w += align_up(RR * 2, 16);
     L.warp_bytes = w;
     L.smem_bytes = (unsigned)(off + emp::DP_WARPS * w);
     if (L.smem_bytes > 227u * 1024u) return fail(-3, "lattice too large for shared memory (row*col)");

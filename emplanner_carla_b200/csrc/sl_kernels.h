@@ -23,7 +23,7 @@ struct DpLaunch {
     int R, C, kmax, n_enr_max, scene_stride, plan_stride, batch;
     // shared-memory carve-up (bytes)
     int off_slab, off_f0, off_nl, off_refc, off_ltab, off_warp, warp_bytes;
-    int w_off_cand, w_off_cost, w_off_rows, w_off_offs, w_off_parent, w_off_sj, w_off_dlon;
+    int w_off_cand, w_off_cost, w_off_rows, w_off_offs, w_off_parent, w_off_sj, w_off_dlon, w_off_k0, w_off_wl;
     unsigned smem_bytes;
 };
 
