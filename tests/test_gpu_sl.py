@@ -195,3 +195,44 @@ def test_pipelined_submit_wait_matches_synchronous_plan():
             pl.plan_submit(1, batches[0], dp, qp, outs[1])        # pageable input
     finally:
         pl.close()
+
+
+def test_dp_bit_exact_at_scale_and_at_the_lattice_limits(planner):
+    """The branch-and-bound DP kernel against the full-sweep oracle: the first 1024 frames of BASELINE configs[1]
+    (rows and cost bit-identical), and the largest lattice the kernel takes (row = EMP_MAX_ROW = 16, 100 columns,
+    16 obstacle slots, sampling_res 1): rows, cost and densified length."""
+    from emplanner_carla_b200 import api, scenes
+    from oracle import sl_dp
+    lat = scenes.LATTICE_C
+    sc = scenes.sl_scenes(4096, lat, 2)
+    big_pl = api.HostPlanner(max_batch=1024, n_enr_max=api.max_enriched(api.dp_params(**lat.kwargs())), max_col=lat.col)
+    try:
+        first = {k: v[:1024] for k, v in sc.items()}
+        view, rows = big_pl.dp(api.pack_scenes(**first), api.dp_params(**lat.kwargs()))
+    finally:
+        big_pl.close()
+    o_rows, _, _, o_cost = sl_dp.dp_batch(first["obs_s"], first["obs_l"], first["nobs"], first["s0"], first["l0"],
+                                          first["dl0"], first["ddl0"], **lat.kwargs())
+    assert np.array_equal(rows, o_rows)
+    has = first["nobs"] > 0
+    assert np.array_equal(view.dp_cost[has], o_cost[has])
+    big = scenes.Lattice("max", 16, 100, 1.0, 1.0, 1)
+    B, K = 12, 16
+    rng = np.random.default_rng(11)
+    obs_s = np.sort(rng.uniform(8.0, 95.0, (B, K)), axis=1)
+    obs_l = rng.uniform(-6.0, 6.0, (B, K))
+    nobs = np.full(B, K, dtype=np.int32)
+    nobs[:3] = [1, 7, 12]
+    s0, l0 = rng.uniform(0, 2, B), rng.uniform(-0.5, 0.5, B)
+    dl0, ddl0 = rng.uniform(-0.05, 0.05, B), rng.uniform(-0.01, 0.01, B)
+    dp = api.dp_params(**big.kwargs())
+    pl = api.HostPlanner(max_batch=B, kmax=16, n_enr_max=api.max_enriched(dp), max_col=big.col)
+    try:
+        view, rows = pl.dp(api.pack_scenes(obs_s, obs_l, nobs, s0, l0, dl0, ddl0, kmax=16), dp)
+    finally:
+        pl.close()
+    o_rows, o_s, o_l, o_cost = sl_dp.dp_batch(obs_s, obs_l, nobs, s0, l0, dl0, ddl0, **big.kwargs())
+    assert np.array_equal(rows, o_rows) and np.array_equal(view.dp_cost, o_cost)
+    for b in range(B):
+        es, el = sl_dp.enrich(o_s[b], o_l[b], s0[b], l0[b], dl0[b], ddl0[b], resolution=1)
+        assert int(view.n_enr[b]) == len(es) and np.abs(view.enr_l[b, :len(es)] - el).max() <= 1e-12

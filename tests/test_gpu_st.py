@@ -123,3 +123,24 @@ def test_st_helpers_dropin_against_reference_golden(planner):
         sys.path.remove(pkg_dir)
         for k in [k for k in sys.modules if k == "planner" or k.startswith("planner.")]:
             del sys.modules[k]
+
+
+def test_sixteen_obstacles_and_pruning_matches_full_sweep(planner):
+    """kmax = 16 obstacle slots (EMP_ST_KMAX), dense scenes where most candidates are blocked: the branch-and-bound
+    kernel against the oracle's full 40x40 sweep - parents, s_dot, end node exact; costs 1e-12 relative."""
+    from emplanner_carla_b200 import api
+    from oracle import st_dp
+    rng = np.random.default_rng(21)
+    B, K = 6, 16
+    s_in = rng.uniform(2.0, 45.0, (B, K))
+    s_out = s_in + rng.uniform(-5.0, 25.0, (B, K))            # some obstacles move backwards
+    t_in = rng.uniform(0.0, 6.0, (B, K))
+    t_out = t_in + rng.uniform(0.3, 3.0, (B, K))
+    s_in[0, 3:] = np.nan                                      # ragged: 3 obstacles only
+    v0 = rng.uniform(1.0, 14.0, B)
+    rec = api.pack_st_scenes(s_in, s_out, t_in, t_out, v0, kmax=16)
+    r = planner.st_dp(rec, api.st_params(), want_tables=True)
+    for f in range(B):
+        o = st_dp.speed_dp(s_in[f], s_out[f], t_in[f], t_out[f], v0[f])
+        _check(r, f, o["cost"], o["s_dot"], o["node"], o["min_row"], o["min_col"])
+        assert np.array_equal(r["dp_s"][f], o["dp_s"], equal_nan=True)
