@@ -105,6 +105,11 @@ struct Factor {                 // per-lane pieces of the KKT factorisation
 // stages with (lane mod 2d) == d-1 are eliminated against their current neighbours lane-d and lane+d, which
 // stay with (lane mod 2d) == 2d-1.  Five levels instead of n-1 sequential steps, every level lane-parallel.
 #define EMP_CR_LEVELS 5
+#ifdef EMP_QP_UNROLL_LEVELS
+#define EMP_LEVEL_UNROLL _Pragma("unroll")
+#else
+#define EMP_LEVEL_UNROLL _Pragma("unroll 1")
+#endif
 
 #ifndef EMP_QP_MINBLOCKS
 #define EMP_QP_MINBLOCKS 2
@@ -321,7 +326,7 @@ sl_qp_kernel(const double *__restrict__ scenes, double *__restrict__ plans, doub
             bool bad = false;
             EMP_UNROLL
             for (int k = 0; k < 9; ++k) { F.xl[k] = 0.0; F.xr[k] = 0.0; }
-#pragma unroll 1
+EMP_LEVEL_UNROLL
             for (int lev = 0; lev < EMP_CR_LEVELS; ++lev) {
                 const int d = 1 << lev, msk = 2 * d - 1;
                 const bool el = (lane & msk) == d - 1;
@@ -398,7 +403,7 @@ sl_qp_kernel(const double *__restrict__ scenes, double *__restrict__ plans, doub
             // forward elimination, level by level: t_i = L_i^-1 r_i, then r_{i-d} -= XL' t_i, r_{i+d} -= XR' t_i
             if (!stage) { r0 = 0.0; r1 = 0.0; r2 = 0.0; }
             double t0 = 0.0, t1 = 0.0, t2 = 0.0;
-#pragma unroll 1
+EMP_LEVEL_UNROLL
             for (int lev = 0; lev < EMP_CR_LEVELS; ++lev) {
                 const int d = 1 << lev, msk = 2 * d - 1;
                 const bool el = (lane & msk) == d - 1;
@@ -421,7 +426,7 @@ sl_qp_kernel(const double *__restrict__ scenes, double *__restrict__ plans, doub
             }
             // back substitution, top level first: y_i = L_i^-T (t_i - XL y_{i-d} - XR y_{i+d})
             double y0 = 0.0, y1 = 0.0, y2 = 0.0;
-#pragma unroll 1
+EMP_LEVEL_UNROLL
             for (int lev = EMP_CR_LEVELS - 1; lev >= 0; --lev) {
                 const int d = 1 << lev, msk = 2 * d - 1;
                 const bool el = (lane & msk) == d - 1;

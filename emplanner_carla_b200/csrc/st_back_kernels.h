@@ -5,7 +5,10 @@
 
 namespace emp {
 
-constexpr int SQP_WARPS = 4;          // frames per CTA of the speed-QP kernel
+#ifndef EMP_SQP_WARPS
+#define EMP_SQP_WARPS 1
+#endif
+constexpr int SQP_WARPS = EMP_SQP_WARPS;   // frames per CTA of the speed-QP kernel (1: every shared-memory address is an immediate)
 constexpr int SQP_MAXQ = 16;          // stations (qp_size <= 16: the DP profile holds 16 entries, one is the NaN terminator)
 constexpr int SQP_NV = 3 * SQP_MAXQ;  // variables
 constexpr int SQP_NE = 2 * (SQP_MAXQ - 1);

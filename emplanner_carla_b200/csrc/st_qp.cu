@@ -39,7 +39,10 @@ struct WarpSmem {
     double ac[12];            // A_sub columns (:444-449)
 };
 
-__global__ void __launch_bounds__(SQP_WARPS * 32)
+#ifndef EMP_SQP_MINBLOCKS
+#define EMP_SQP_MINBLOCKS (SQP_WARPS == 1 ? 8 : 2)
+#endif
+__global__ void __launch_bounds__(SQP_WARPS * 32, EMP_SQP_MINBLOCKS)
 speed_qp_kernel(const double *__restrict__ start, const double *__restrict__ st_out, const double *__restrict__ bounds,
                 double *__restrict__ out, int32_t *__restrict__ status_iters, const SpeedQpLaunch p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -198,8 +201,10 @@ speed_qp_kernel(const double *__restrict__ start, const double *__restrict__ st_
                 const double a1 = W.Y[r * YS + lane];
                 const int lim = 2 * (r / 3 + 1);                     // Y[r][c] = 0 for columns of later stations
                 EMP_UNROLL
-                for (int c = 0; c < NE; ++c)
-                    if (c < lim) acc[c] = fma(a1, W.Y[r * YS + c], acc[c]);
+                for (int c = 0; c < NE; ++c) {
+                    if (c >= lim) break;                             // uniform
+                    acc[c] = fma(a1, W.Y[r * YS + c], acc[c]);
+                }
             }
             EMP_UNROLL
             for (int c = 0; c < NE; ++c)
