@@ -25,6 +25,26 @@ namespace {
 constexpr int NQP = EMP_ST_QP_POINTS;
 constexpr int MAXQ = SQP_MAXQ, NV = SQP_NV, NE = SQP_NE, YS = SQP_YS, KS = SQP_KS;
 
+// reciprocal / reciprocal square root: hardware seed + two Newton steps (full double precision for the well-scaled
+// arguments met here; the QP's parity bar is 1e-4 m on the solution, the iterates agree to ~1e-9)
+__device__ __forceinline__ double frcp(double x) {
+    double y;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    double e = fma(-x, y, 1.0);
+    y = fma(y, e, y);
+    e = fma(-x, y, 1.0);
+    return fma(y, e, y);
+}
+__device__ __forceinline__ double frsqrt(double x) {
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    const double hx = 0.5 * x;
+    double e = fma(-hx * y, y, 0.5);
+    y = fma(y, e, y);
+    e = fma(-hx * y, y, 0.5);
+    return fma(y, e, y);
+}
+
 struct WarpSmem {
     double Y[NV * YS];        // L^-1 A'
     double K[NE * KS];        // A S^-1 A', overwritten by its Cholesky factor (strict lower part)
@@ -170,7 +190,7 @@ speed_qp_kernel(const double *__restrict__ start, const double *__restrict__ st_
             for (int k = 0; k < q; ++k) {
                 const double dd = W.dg[lane][k] - prev * prev;
                 bad = bad || !(dd > 0.0);
-                const double inv = 1.0 / sqrt(dd);
+                const double inv = frsqrt(dd);
                 const double e = k < q - 1 ? (lane == 0 ? -W.wm[k] : lane == 2 ? -wj2 : 0.0) * inv : 0.0;
                 W.ldi[lane][k] = inv;
                 W.le[lane][k] = e;
@@ -214,7 +234,7 @@ speed_qp_kernel(const double *__restrict__ start, const double *__restrict__ st_
         for (int j = 0; j < ne; ++j) {
             const double djj = W.K[j * KS + j];
             if (!(djj > 0.0)) return true;                            // uniform
-            const double inv = 1.0 / sqrt(djj);
+            const double inv = frsqrt(djj);
             double lij = 0.0;
             if (lane > j && lane < ne) {
                 lij = W.K[lane * KS + j] * inv;
@@ -381,8 +401,9 @@ speed_qp_kernel(const double *__restrict__ start, const double *__restrict__ st_
             if (!isfinite((gap + resx) + resz)) { status = EMP_QP_UNKNOWN_NUMERIC; break; }
             if (it > 0 && gap > gap_limit) { status = EMP_QP_UNKNOWN_NUMERIC; break; }
 
+            double is[5];
             EMP_UNROLL
-            for (int r = 0; r < 5; ++r) w[r] = on[r] ? z[r] / s[r] : 0.0;
+            for (int r = 0; r < 5; ++r) { is[r] = frcp(s[r]); w[r] = on[r] ? z[r] * is[r] : 0.0; }
             if (factor(w)) { status = EMP_QP_UNKNOWN_NUMERIC; break; }
             const double mu = gap / (double)m_rows;
             double sigma = 0.0, step = 1.0, dyv = 0.0;
@@ -391,7 +412,7 @@ speed_qp_kernel(const double *__restrict__ start, const double *__restrict__ st_
                 EMP_UNROLL
                 for (int r = 0; r < 5; ++r) {
                     const double bs = (sigma * mu - s[r] * z[r]) - (pass == 1 ? ws3[r] : 0.0);
-                    tq[r] = on[r] ? (bs + z[r] * rz[r]) / s[r] : 0.0;
+                    tq[r] = on[r] ? (bs + z[r] * rz[r]) * is[r] : 0.0;
                 }
                 __syncwarp();
                 if (lane < MAXQ) W.wm[lane] = on[4] ? tq[4] : 0.0;
@@ -408,7 +429,7 @@ speed_qp_kernel(const double *__restrict__ start, const double *__restrict__ st_
                     dsv[r] = -rz[r] - g[r];
                     if (on[r]) {
                         dsdz += dsv[r] * dz[r];
-                        tmax = fmax(tmax, fmax(-dsv[r] / s[r], -dz[r] / z[r]));
+                        tmax = fmax(tmax, fmax(-dsv[r] * is[r], -dz[r] * frcp(z[r])));
                     }
                     if (pass == 0) ws3[r] = on[r] ? dsv[r] * dz[r] : 0.0;
                 }
