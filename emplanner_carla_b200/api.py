@@ -541,25 +541,32 @@ class EmCycle:
                         qp=f64(B, 4, ST_QP_POINTS), qp_status_iters=i32(B, 2), dense=f64(B, 4, ST_DENSE),
                         dense_status=i32(B), traj=f64(B, 7, ST_DENSE), merge_status=i32(B))
 
-    def run(self, sl_scenes, st_scenes, start, current_time):
+    def run(self, sl_scenes, st_scenes, start, current_time, mark=None):
         """sl_scenes [B, 6+2*sl_kmax], st_scenes [B, 2+4*st_kmax], start [B,2] = (s_dot, s_dot2), current_time [B]:
-        contiguous float64 CUDA tensors.  Enqueues the cycle and returns the buffer dict."""
+        contiguous float64 CUDA tensors.  Enqueues the cycle and returns the buffer dict.  `mark(name)` is called
+        after every stage has been enqueued (benchmarks record CUDA events there)."""
         L, sp, b, B, p = _lib.lib(), _stream_ptr(), self.buf, self.B, _dev_ptr
         ck = _lib.check
+        mark = mark or (lambda name: None)
         ck(L.emp_sl_plan_dev(p(sl_scenes), self.sl_kmax, B, C.byref(self.dp), C.byref(self.qp), self.NE, p(b["plans"]),
                              None, sp))
+        mark("sl_dp+sl_qp")
         ck(L.emp_cycle_path_points_dev(p(b["plans"]), self.NE, B, self.MP, p(b["xy"]), p(b["npts"]), sp))
         ck(L.emp_smooth_line_dev(p(b["xy"]), p(b["npts"]), self.MP, B, C.byref(self.sm), p(b["cart"]),
                                  p(b["smooth_status_iters"]), sp))
         ck(L.emp_cycle_path_tables_dev(p(b["cart"]), p(b["npts"]), self.MP, B, self.NP, p(b["path2"]), p(b["path5"]), sp))
+        mark("path glue + smooth_reference_line")
         ck(L.emp_st_dp_dev(p(st_scenes), self.st_kmax, B, C.byref(self.st), p(b["st_out"]), None, None, None, sp))
+        mark("st_dp")
         ck(L.emp_st_convex_space_dev(p(b["st_out"]), p(st_scenes), self.st_kmax, p(b["path2"]), self.NP, C.byref(self.sq),
                                      B, p(b["bounds"]), p(b["convex_status"]), sp))
         ck(L.emp_st_speed_qp_dev(p(start), p(b["st_out"]), p(b["bounds"]), B, C.byref(self.sq), p(b["qp"]),
                                  p(b["qp_status_iters"]), sp))
+        mark("convex_space + speed_qp")
         ck(L.emp_st_increase_points_dev(p(b["qp"]), B, p(b["dense"]), p(b["dense_status"]), sp))
         ck(L.emp_st_path_speed_merge_dev(p(b["dense"]), p(current_time), p(b["path5"]), self.NP, B, p(b["traj"]),
                                          p(b["merge_status"]), sp))
+        mark("increase_points + path_speed_merge")
         return b
 
     N_LAUNCHES = 10

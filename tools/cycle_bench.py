@@ -78,6 +78,17 @@ def main():
         return float(t.item()) / args.steps
 
     ms_cycle = timed(lambda: pack_and_gather(cyc.run(sl_d, st_d, start_d, now_d)))
+    stages = []                                            # per-stage share of one cycle (CUDA events between the stages)
+    ev = [torch.cuda.Event(enable_timing=True)]
+    ev[0].record(stream)
+    def mark(name):
+        e = torch.cuda.Event(enable_timing=True)
+        e.record(stream)
+        stages.append(name)
+        ev.append(e)
+    cyc.run(sl_d, st_d, start_d, now_d, mark=mark)
+    torch.cuda.synchronize()
+    stage_ms = {n: round(ev[i].elapsed_time(ev[i + 1]), 4) for i, n in enumerate(stages)}
     st_out = torch.empty((B, api.ST_OUT_STRIDE), dtype=torch.float64, device=dev)
     ms_st = timed(lambda: api.st_dp_device(st_d, cyc.st, st_out))
     if rank == 0:
@@ -91,7 +102,7 @@ def main():
                               ms_per_step=ms_cycle,
                               config={"workload": "BASELINE configs[4]: batch=%d full EM cycle, lattice %s, %d-way frame shard, "
                                       "NCCL all-gather of result records" % (B * world, lat.name, world),
-                                      "gpu_launches_per_step": api.EmCycle.N_LAUNCHES,
+                                      "gpu_launches_per_step": api.EmCycle.N_LAUNCHES, "stage_ms_rank0": stage_ms,
                                       "frames_finishing_whole_cycle": float(done.mean()),
                                       "sl_qp_optimal": float((view.qp_status == 0).mean()),
                                       "st_full_profile_index_error": float((h["qp_status_iters"][:, 0] == api.ST_INDEX_ERROR).mean())})))
