@@ -41,9 +41,9 @@ SCENE_BYTES = 164
 # Static ncu facts of the current kernels (one `ncu --set full` capture per change, see profiles/): the FP64 pipe
 # utilisation is the compute-roofline fraction; dram bytes per launch (batch 4096) go into roofline.traffic.
 NCU_STATIC = {
-    "C_60x11": {"fp64_pipe_active": {"sl_dp_kernel": 0.222, "sl_qp_kernel": 0.381},
-                "issue_active": {"sl_dp_kernel": 0.613, "sl_qp_kernel": 0.432},
-                "dram_bytes_per_launch": {"sl_dp_kernel": 3959040 + 218880, "sl_qp_kernel": 5505792},
+    "C_60x11": {"fp64_pipe_active": {"sl_dp_kernel": 0.213, "sl_qp_kernel": 0.381},
+                "issue_active": {"sl_dp_kernel": 0.609, "sl_qp_kernel": 0.434},
+                "dram_bytes_per_launch": {"sl_dp_kernel": 919040 + 107520, "sl_qp_kernel": 5506048},
                 "source": "profiles/r1_ncu_sl_final_summary.txt (batch 4096, lattice C, serial pass)"},
 }
 
