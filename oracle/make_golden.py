@@ -137,9 +137,9 @@ def make_frenet():
 
 def make_st():
     _, _, spt = refshim.modules()
-    F = 4
+    F = 16
     sc = scenes.st_scenes(F, 3, k_fixed=None)
-    sc["nobs"][:] = [8, 3, 0, 5]
+    sc["nobs"][:4] = [8, 3, 0, 5]                           # the rest: the generator's own 0..8
     act = np.arange(scenes.KMAX)[None, :] < sc["nobs"][:, None]
     for k in ("s_in", "s_out", "t_in", "t_out"):
         full = scenes.st_scenes(F, 3)[k]
