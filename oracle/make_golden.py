@@ -338,7 +338,7 @@ def main(argv):
                      s0=np.array([0.5]), l0=np.array([0.1]), dl0=np.array([0.01]), ddl0=np.array([0.0]))
         make_sl("B", scenes.LATTICE_B, 1, 15, extra=extra)
     if "C" in what:
-        make_sl("C", scenes.LATTICE_C, 2, 48)
+        make_sl("C", scenes.LATTICE_C, 2, 96)
     if "frenet" in what:
         make_frenet()
     if "st" in what:
