@@ -415,6 +415,17 @@ def main():
                "sample": "%d-frame prefix of the batch (%d per core), numpy float64 oracle port of DP->corridor->QP, "
                          "%.1f s wall, DP share of CPU time %.0f%%" % (f, per_core, wall, 100 * dp_share)}
 
+    if cpu:
+        # the unmodified reference's own DP time per frame, recorded while the golden fixtures were generated in the
+        # build container (the reference is Python that cannot travel to the GPU box): context, not a measurement here
+        try:
+            gsec = np.load(os.path.join(ROOT, "tests", "golden", "sl_%s.npz" % args.lattice))["ref_dp_seconds"]
+            cpu["reference_python"] = {"dp_seconds_per_frame_one_core": float(np.mean(gsec)), "frames": int(len(gsec)),
+                                       "where": "build container, tests/golden/sl_%s.npz:ref_dp_seconds "
+                                                "(DP_algorithm only; its QP needs cvxopt)" % args.lattice}
+        except Exception:
+            pass
+
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": t_all / args.steps, "higher_is_better": True,
