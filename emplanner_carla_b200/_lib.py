@@ -109,6 +109,7 @@ _SIGNATURES = {
     "emp_ipc_close": (C.c_int, [_P]),
     "emp_quintic_host": (C.c_int, [_P, _P, C.c_int, _P]),
     "emp_edge_cost_host": (C.c_int, [_P, _P, C.c_int, _P, _P, C.c_int, _DPP, _P]),
+    "emp_edge_cost_ex_host": (C.c_int, [_P, _P, C.c_int, _P, _P, C.c_int, _DPP, C.c_double, C.c_double, _P]),
     "emp_obs_cost_host": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double, _P]),
     "emp_enrich_host": (C.c_int, [_P, _P, _P, _P, C.c_int, C.c_int, C.c_double, C.c_int, _P, _P, _P]),
     "emp_misc_host": (C.c_int, [_P, C.c_int, _P, C.c_int, C.c_int, C.POINTER(MiscAux), _P]),

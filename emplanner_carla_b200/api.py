@@ -292,15 +292,16 @@ class HostPlanner:
         _lib.check(_lib.lib().emp_quintic_host(self._h, _ptr(conds), conds.shape[0], _ptr(out)))
         return out
 
-    def edge_cost(self, edges, obs_s, obs_l, dp):
+    def edge_cost(self, edges, obs_s, obs_l, dp, danger_dis=4, safe_dis=6):
         """cal_start_cost / cal_neighbor_cost for rows (start_s, start_l, start_dl, start_ddl, end_s, end_l)."""
         edges = np.ascontiguousarray(edges, dtype=np.float64).reshape(-1, 6)
         obs_s = np.ascontiguousarray(obs_s, dtype=np.float64).reshape(-1)
         obs_l = np.ascontiguousarray(obs_l, dtype=np.float64).reshape(-1)
         out = np.zeros(edges.shape[0])
         k = obs_s.shape[0]
-        _lib.check(_lib.lib().emp_edge_cost_host(self._h, _ptr(edges), edges.shape[0], _ptr(obs_s) if k else None,
-                                                 _ptr(obs_l) if k else None, k, C.byref(dp), _ptr(out)))
+        _lib.check(_lib.lib().emp_edge_cost_ex_host(self._h, _ptr(edges), edges.shape[0], _ptr(obs_s) if k else None,
+                                                    _ptr(obs_l) if k else None, k, C.byref(dp), float(danger_dis),
+                                                    float(safe_dis), _ptr(out)))
         return out
 
     def obs_cost(self, square_d, w_collision, danger_dis=4, safe_dis=6):

@@ -712,6 +712,11 @@ int emp_quintic_host(EmpPlanner *pl, const double *in, int n, double *out) {
 
 int emp_edge_cost_host(EmpPlanner *pl, const double *edges, int n_edges, const double *obs_s, const double *obs_l,
                        int n_obs, const EmpDpParams *p, double *out) {
+    return emp_edge_cost_ex_host(pl, edges, n_edges, obs_s, obs_l, n_obs, p, 4.0, 6.0, out);   // path_planning.py:588
+}
+
+int emp_edge_cost_ex_host(EmpPlanner *pl, const double *edges, int n_edges, const double *obs_s, const double *obs_l,
+                          int n_obs, const EmpDpParams *p, double danger_dis, double safe_dis, double *out) {
     if (!pl || !edges || !out || !p) return fail(-1, "NULL argument");
     if (n_edges <= 0) return n_edges == 0 ? 0 : fail(-2, "bad n_edges");
     if (n_obs < 0 || (n_obs > 0 && (!obs_s || !obs_l))) return fail(-2, "bad obstacle list");
@@ -722,7 +727,8 @@ int emp_edge_cost_host(EmpPlanner *pl, const double *edges, int n_edges, const d
         const double *d_os = t.in(obs_s, (size_t)n_obs), *d_ol = t.in(obs_l, (size_t)n_obs);
         double *d_out = t.out<double>((size_t)n_edges);
         if (t.err != cudaSuccess) return fail_cuda(t.err, "edge_cost staging");
-        emp::EdgeParams P{p->sample_s, p->w_collision, p->w_smooth[0], p->w_smooth[1], p->w_smooth[2], p->w_ref};
+        emp::EdgeParams P{p->sample_s, p->w_collision, p->w_smooth[0], p->w_smooth[1], p->w_smooth[2], p->w_ref,
+                           danger_dis * danger_dis, safe_dis * safe_dis};
         EMP_CK(emp::launch_edge_cost(d_e, d_os, d_ol, n_obs, n_edges, P, d_out, pl->stream), "edge_cost launch");
         t.back(out, d_out, (size_t)n_edges);
         if (t.err != cudaSuccess) return fail_cuda(t.err, "edge_cost copy-back");

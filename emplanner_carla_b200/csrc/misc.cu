@@ -108,7 +108,7 @@ __global__ void edge_cost_kernel(const double *__restrict__ edges, const double 
             const double dlon = obs_s[o] - sm[m], dlat = obs_l[o] - lm[m];
             d2[m] = dlon * dlon + dlat * dlat;
         }
-        coll = coll + obs_cost_seq(d2, NS, 1, P.w_col, 16.0, 36.0);
+        coll = coll + obs_cost_seq(d2, NS, 1, P.w_col, P.danger2, P.safe2);
     }
     out[i] = (smooth + coll) + P.w_ref * sl2;
 }

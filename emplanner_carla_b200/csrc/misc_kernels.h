@@ -5,7 +5,7 @@
 
 namespace emp {
 
-struct EdgeParams { double sample_s, w_col, w0, w1, w2, w_ref; };
+struct EdgeParams { double sample_s, w_col, w0, w1, w2, w_ref, danger2, safe2; };
 
 cudaError_t launch_quintic(const double *in, double *out, int n, cudaStream_t st);
 cudaError_t launch_obs_cost(const double *d2, int n, int batch, double w, double danger2, double safe2, double *out,

@@ -294,6 +294,10 @@ int emp_cycle_path_tables_dev(const double *cart, const int32_t *npts, int max_p
 int emp_quintic_host(EmpPlanner *pl, const double *in, int n, double *out);
 int emp_edge_cost_host(EmpPlanner *pl, const double *edges, int n_edges, const double *obs_s, const double *obs_l,
                        int n_obs, const EmpDpParams *p, double *out);
+/* emp_edge_cost_ex_host: the same edge cost with explicit danger / safe distances: planner/speed_planning.py
+ *                     cal_start_cost (:96-169) is that function on an (s, t) quintic with cal_obs_cost's (:172) 3 / 5. */
+int emp_edge_cost_ex_host(EmpPlanner *pl, const double *edges, int n_edges, const double *obs_s, const double *obs_l,
+                          int n_obs, const EmpDpParams *p, double danger_dis, double safe_dis, double *out);
 int emp_obs_cost_host(EmpPlanner *pl, const double *square_d, int n, int batch, double w_collision, double danger_dis,
                       double safe_dis, double *out);
 int emp_enrich_host(EmpPlanner *pl, const double *node_s, const double *node_l, const double *start, int C, int batch,

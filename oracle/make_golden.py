@@ -322,12 +322,44 @@ def make_st_back(n_frames=128, n_dense=6):
           int(rec["matrices_identical"].sum()), int(rec["qp_optimal"].sum())))
 
 
+def make_speed_stub():
+    """planner/speed_planning.py: what runs (cal_start_cost, cal_obs_cost) and how the entry point fails."""
+    sp = refshim.speed_planning_module()
+    rng = np.random.default_rng(scenes.BASE_SEED + 400)
+    n = 24
+    rec = dict(begin=np.stack([rng.uniform(0, 20, n), rng.uniform(0, 1, n), rng.uniform(0, 0.2, n)], 1),
+               end=np.zeros((n, 2)), sample_t=rng.uniform(0.5, 2.0, n), obs_s=rng.uniform(2, 40, (n, 3)),
+               obs_t=rng.uniform(0, 6, (n, 3)), cost=np.zeros(n))
+    rec["end"][:, 0] = rec["begin"][:, 0] + rng.uniform(3, 12, n)
+    rec["end"][:, 1] = rec["begin"][:, 1] + rng.uniform(0.5, 3, n)
+    rec["obs_s"][:6] = rec["begin"][:6, :1] + rng.uniform(0, 3, (6, 3))       # some inside the 3 m / 5 m zones
+    rec["obs_t"][:6] = rec["begin"][:6, 1:2] + rng.uniform(0, 2, (6, 3))
+    w = (1e10, [300, 2000, 10000], 20)                                         # the stub's own weights (:83-85)
+    for i in range(n):
+        rec["cost"][i] = float(sp.cal_start_cost(list(rec["obs_s"][i]), list(rec["obs_t"][i]), *rec["begin"][i],
+                                                 *rec["end"][i], rec["sample_t"][i], *w))
+    d2 = np.array([30.0, 24.0, 16.0, 9.0, 4.0, 50.0, 20.0, 20.0, 20.0, 20.0])
+    rec["obs_cost_d2"] = d2
+    rec["obs_cost"] = np.array([sp.cal_obs_cost(1e10, d2.reshape(10, 1)), sp.cal_obs_cost(7.0, np.full((10, 1), 25.0)),
+                                sp.cal_obs_cost(3.0, d2.reshape(10, 1), danger_dis=1, safe_dis=6)])
+    exc = []
+    for obs_pos in ([12.0], []):
+        try:
+            sp.construct_ST_graph_and_planning([0.0], 0, 5, 0, obs_pos, [3.0] * len(obs_pos))
+            exc.append("returned")
+        except Exception as e:
+            exc.append(type(e).__name__)
+    rec["entry_point_exceptions"] = np.array(exc)
+    np.savez_compressed(os.path.join(GOLDEN, "speed_stub.npz"), ref_commit=REF_COMMIT, **rec)
+    print("speed_stub done:", exc)
+
+
 def _rng_a0(n):
     return np.random.default_rng(scenes.BASE_SEED + 300).uniform(-1.0, 1.0, n)
 
 
 def main(argv):
-    what = argv or ["A", "B", "C", "frenet", "st", "st_misc", "st_back"]
+    what = argv or ["A", "B", "C", "frenet", "st", "st_misc", "st_back", "speed_stub"]
     os.makedirs(GOLDEN, exist_ok=True)
     if "A" in what:
         make_sl("A", scenes.LATTICE_A, 0, 192)
@@ -347,6 +379,8 @@ def main(argv):
         make_st_misc()
     if "st_back" in what:
         make_st_back()
+    if "speed_stub" in what:
+        make_speed_stub()
 
 
 if __name__ == "__main__":

@@ -128,3 +128,26 @@ def modules():
         sys.path.remove(REFERENCE_ROOT)
     _mods = mods
     return mods
+
+
+def speed_planning_module():
+    """The reference's planner/speed_planning.py (the non-running S-T stub), imported like modules()."""
+    install()
+    modules()
+    import importlib
+    def _is_ref(mod):
+        f = getattr(mod, "__file__", None)
+        if f:
+            return f.startswith(REFERENCE_ROOT)
+        return any(str(p).startswith(REFERENCE_ROOT) for p in getattr(mod, "__path__", []))
+    saved = {k: sys.modules.pop(k) for k in list(sys.modules)
+             if (k == "planner" or k.startswith("planner.")) and not _is_ref(sys.modules[k])}
+    sys.path.insert(0, REFERENCE_ROOT)
+    try:
+        mod = importlib.import_module("planner.speed_planning")
+    finally:
+        for k in [k for k in sys.modules if k == "planner" or k.startswith("planner.")]:
+            del sys.modules[k]
+        sys.modules.update(saved)
+        sys.path.remove(REFERENCE_ROOT)
+    return mod

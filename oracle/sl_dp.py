@@ -151,9 +151,10 @@ def quintic_closed(l0, dl0, ddl0, l1, dl1, ddl1, s0, s1):
             a[5]]
 
 
-def edge_cost_closed(obs_s, obs_l, s0, l0, dl0, ddl0, s1, l1, sample_s, w_col, w_s, w_ref):
+def edge_cost_closed(obs_s, obs_l, s0, l0, dl0, ddl0, s1, l1, sample_s, w_col, w_s, w_ref, danger2=DANGER2, safe2=SAFE2):
     """One edge in closed form (what csrc/misc.cu::edge_cost_kernel and column 0 of K1 compute):
-    cal_start_cost / cal_neighbor_cost (path_planning.py:435-585) with the quintic evaluated in u = s - s0."""
+    cal_start_cost / cal_neighbor_cost (path_planning.py:435-585) with the quintic evaluated in u = s - s0.
+    danger2 / safe2 = 9 / 25 gives planner/speed_planning.py cal_start_cost (:96-169) on an (s, t) quintic."""
     T = s1 - s0
     iT = 1.0 / T
     iT3 = (iT * iT) * iT
@@ -187,10 +188,10 @@ def edge_cost_closed(obs_s, obs_l, s0, l0, dl0, ddl0, s1, l1, sample_s, w_col, w
         for m in range(NSAMP):
             dlon, dlat = obs_s[o] - sm[m], obs_l[o] - lm[m]
             d2 = dlon * dlon + dlat * dlat
-            if d2 <= DANGER2:
+            if d2 <= danger2:
                 one = one + w_col
                 break
-            elif d2 < SAFE2:
+            elif d2 < safe2:
                 one = one + NEAR_COST / d2
         coll = coll + one
     return (smooth + coll) + w_ref * sl2

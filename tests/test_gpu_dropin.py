@@ -163,3 +163,26 @@ def test_predict_block_based_on_frenet_and_cal_proj_point_1(planner_pkg):
     assert np.allclose(got, want, rtol=0, atol=1e-9)
     r1 = planning_utils.cal_proj_point_1(s, 0, line, smap)
     assert np.allclose(r1[:4], ofr.proj_point(s, 0, line, smap)[:4], rtol=0, atol=1e-9) and r1[4] == idx
+
+
+def test_speed_planning_stub_dropin(planner_pkg):
+    """`from planner import speed_planning` resolves to the drop-in: cal_start_cost / cal_obs_cost against outputs of
+    the unmodified reference (tests/golden/speed_stub.npz; 1e-9 relative = the noise of the reference's 6x6
+    inverse, and bit-exact against the oracle's closed form), the entry point raises what the reference raises."""
+    from oracle import sl_dp
+    from planner import speed_planning as sp
+    g = load_golden("speed_stub.npz")
+    w = (1e10, [300, 2000, 10000], 20)
+    for i in range(len(g["cost"])):
+        b, e = g["begin"][i], g["end"][i]
+        got = sp.cal_start_cost(list(g["obs_s"][i]), list(g["obs_t"][i]), b[0], b[1], b[2], e[0], e[1], g["sample_t"][i], *w)
+        assert got.shape == (1, 1) and abs(got[0, 0] - g["cost"][i]) <= 1e-9 * abs(g["cost"][i])
+        assert got[0, 0] == sl_dp.edge_cost_closed(list(g["obs_s"][i]), list(g["obs_t"][i]), b[0], b[1], b[2], 0.0, e[0],
+                                                   e[1], g["sample_t"][i], w[0], w[1], w[2], danger2=9.0, safe2=25.0)
+    d2 = g["obs_cost_d2"].reshape(10, 1)
+    assert sp.cal_obs_cost(1e10, d2) == g["obs_cost"][0] and sp.cal_obs_cost(7.0, np.full((10, 1), 25.0)) == g["obs_cost"][1]
+    assert sp.cal_obs_cost(3.0, d2, danger_dis=1, safe_dis=6) == g["obs_cost"][2]
+    with pytest.raises(TypeError):
+        sp.construct_ST_graph_and_planning([0.0], 0, 5, 0, [12.0], [3.0])
+    with pytest.raises(NameError):
+        sp.construct_ST_graph_and_planning([0.0], 0, 5, 0, [], [])

@@ -218,3 +218,22 @@ def test_speed_qp_repair_is_a_valid_qp_solution():
     assert np.abs(A @ x - b).max() < 1e-6 and (G @ x - h).max() < 1e-6
     assert np.abs(P @ x + q + A.T @ info["y"] + G.T @ info["z"]).max() < 1e-4 * max(1.0, np.abs(q).max())
     assert info["z"].min() > -1e-9 and abs(info["z"] @ (h - G @ x)) < 1e-5 * abs(info["pcost"])   # reltol 1e-6
+
+
+def test_speed_planning_stub_oracle_against_reference_golden():
+    """planner/speed_planning.py (the stub the north_star names): cal_start_cost is the S-L edge cost on an (s, t)
+    quintic with 3 m / 5 m distances - oracle closed form vs the unmodified reference (whose 6x6 inverse is noisy:
+    1e-9 relative); cal_obs_cost exact; the entry point raises TypeError / NameError in the reference."""
+    g = load_golden("speed_stub.npz")
+    w = (1e10, [300, 2000, 10000], 20)
+    hit = 0
+    for i in range(len(g["cost"])):
+        b, e = g["begin"][i], g["end"][i]
+        got = sl_dp.edge_cost_closed(list(g["obs_s"][i]), list(g["obs_t"][i]), b[0], b[1], b[2], 0.0, e[0], e[1],
+                                     g["sample_t"][i], w[0], w[1], w[2], danger2=9.0, safe2=25.0)
+        assert abs(got - g["cost"][i]) <= 1e-9 * abs(g["cost"][i]), i
+        hit += g["cost"][i] >= 1e10
+    assert hit >= 2                                            # collisions are exercised
+    assert list(g["entry_point_exceptions"]) == ["TypeError", "NameError"]
+    d2 = g["obs_cost_d2"]
+    assert g["obs_cost"][0] == 5000 / 24.0 + 5000 / 16.0 + 1e10 and g["obs_cost"][1] == 0.0
