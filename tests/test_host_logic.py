@@ -116,3 +116,22 @@ def test_wire_format_round_trip_and_errors():
     assert np.array_equal(rep["path"], path) and list(rep["match_point_list"]) == [17, 3] and rep["path_l"][5] == -5.0
     xy, n = wire.stack_obstacles([r, r2], kmax=4)
     assert xy.shape == (2, 4, 2) and list(n) == [2, 0] and xy[0, 1, 1] == -4.25 and np.isnan(xy[1]).all()
+
+
+def test_speed_qp_kernel_linear_algebra_model_reproduces_the_oracle_iterates():
+    """csrc/st_qp.cu's structured KKT solve (three tridiagonal chains + dense K), modelled in numpy and plugged into
+    the oracle's coneqp iteration, gives the oracle's own status, iteration count and solution on golden frames."""
+    from oracle import coneqp, st_back
+    from speed_qp_model import ChainKkt
+    g = load_golden("st_back.npz")
+    frames = np.nonzero(g["matrices_identical"] == 1)[0][:10]
+    assert len(frames) >= 8
+    for f in frames:
+        m = st_back.speed_qp_matrices(g["v0"][f], g["a0"][f], g["dp_s"][f], g["dp_t"][f], *g["ref_bounds"][f])
+        P, q, G, h, A, b = st_back.speed_qp_cone_form(m)
+        want = coneqp.qp(P, q, G, h, A, b)
+        got = coneqp.qp(P, q, G, h, A, b, kkt=ChainKkt(P, G, A))
+        assert got["status"] == want["status"]
+        if want["status"] == "optimal":
+            assert got["iterations"] == want["iterations"]
+            assert np.abs(got["x"] - want["x"]).max() <= 1e-7 * max(1.0, np.abs(want["x"]).max())
