@@ -24,7 +24,7 @@ class QpParams(C.Structure):
                 ("w_dddl", C.c_double), ("w_centre", C.c_double), ("w_end_l", C.c_double), ("w_end_dl", C.c_double),
                 ("w_end_ddl", C.c_double), ("host_d1", C.c_double), ("host_d2", C.c_double), ("host_w", C.c_double),
                 ("obs_length", C.c_double), ("obs_width", C.c_double), ("abstol", C.c_double), ("reltol", C.c_double),
-                ("feastol", C.c_double), ("maxiters", C.c_int32), ("reserved", C.c_int32)]
+                ("feastol", C.c_double), ("maxiters", C.c_int32), ("reserved", C.c_int32), ("diverge_factor", C.c_double)]
 
 
 class StParams(C.Structure):
@@ -37,14 +37,15 @@ class SmoothParams(C.Structure):
     """EmpSmoothParams: smooth_reference_line keyword defaults (reference planning_utils.py:262-264)."""
     _fields_ = [("w_smooth", C.c_double), ("w_length", C.c_double), ("w_ref", C.c_double), ("x_thre", C.c_double),
                 ("y_thre", C.c_double), ("abstol", C.c_double), ("reltol", C.c_double), ("feastol", C.c_double),
-                ("maxiters", C.c_int32), ("heading_only", C.c_int32)]
+                ("maxiters", C.c_int32), ("heading_only", C.c_int32), ("diverge_factor", C.c_double)]
 
 
 class SpeedQpParams(C.Structure):
     """EmpSpeedQpParams: speed_QP / generate_convex_space keyword defaults (speed_planning_test.py:403-404, :309)."""
     _fields_ = [("w_s_dot2", C.c_double), ("w_v_ref", C.c_double), ("w_jerk", C.c_double),
                 ("reference_speed", C.c_double), ("max_lateral_accel", C.c_double), ("abstol", C.c_double),
-                ("reltol", C.c_double), ("feastol", C.c_double), ("maxiters", C.c_int32), ("reserved", C.c_int32)]
+                ("reltol", C.c_double), ("feastol", C.c_double), ("maxiters", C.c_int32), ("reserved", C.c_int32),
+                ("diverge_factor", C.c_double)]
 
 
 class MiscAux(C.Structure):
@@ -163,7 +164,8 @@ def dp_params(sampling_res=2, w_collision_cost=1e12, w_smooth_cost=(300, 1000, 5
 
 def qp_params(dp_sampling_res=2, w_cost_l=1000, w_cost_dl=10000, w_cost_ddl=3000, w_cost_dddl=150,
               w_cost_centre=250, w_cost_end_l=40, w_cost_end_dl=40, w_cost_end_ddl=40, host_d1=3, host_d2=3,
-              host_w=3, obs_length=5, obs_width=5, abstol=1e-7, reltol=1e-6, feastol=1e-7, maxiters=100):
+              host_w=3, obs_length=5, obs_width=5, abstol=1e-7, reltol=1e-6, feastol=1e-7, maxiters=100,
+              diverge_factor=2.0):
     p = QpParams()
     p.dp_sampling_res = float(dp_sampling_res)
     p.w_l, p.w_dl, p.w_ddl, p.w_dddl = float(w_cost_l), float(w_cost_dl), float(w_cost_ddl), float(w_cost_dddl)
@@ -173,6 +175,7 @@ def qp_params(dp_sampling_res=2, w_cost_l=1000, w_cost_dl=10000, w_cost_ddl=3000
     p.obs_length, p.obs_width = float(obs_length), float(obs_width)
     p.abstol, p.reltol, p.feastol = float(abstol), float(reltol), float(feastol)
     p.maxiters = int(maxiters)
+    p.diverge_factor = float(diverge_factor or 0.0)
     return p
 
 
@@ -184,19 +187,22 @@ def st_params(reference_speed=50, w_cost_ref_speed=4000, w_cost_accel=100, w_cos
 
 
 def speed_qp_params(w_cost_s_dot2=10, w_cost_v_ref=50, w_cost_jerk=500, reference_speed=50,
-                    max_lateral_accel=0.2 * 9.8, abstol=1e-7, reltol=1e-6, feastol=1e-7, maxiters=100):
+                    max_lateral_accel=0.2 * 9.8, abstol=1e-7, reltol=1e-6, feastol=1e-7, maxiters=100,
+                    diverge_factor=2.0):
     p = SpeedQpParams()
     p.w_s_dot2, p.w_v_ref, p.w_jerk = float(w_cost_s_dot2), float(w_cost_v_ref), float(w_cost_jerk)
     p.reference_speed, p.max_lateral_accel = float(reference_speed), float(max_lateral_accel)
     p.abstol, p.reltol, p.feastol, p.maxiters = float(abstol), float(reltol), float(feastol), int(maxiters)
+    p.diverge_factor = float(diverge_factor or 0.0)
     return p
 
 
 def smooth_params(w_cost_smooth=0.4, w_cost_length=0.3, w_cost_ref=0.3, x_thre=0.2, y_thre=0.2,
-                  abstol=1e-7, reltol=1e-6, feastol=1e-7, maxiters=100, heading_only=False):
+                  abstol=1e-7, reltol=1e-6, feastol=1e-7, maxiters=100, heading_only=False, diverge_factor=2.0):
     p = SmoothParams()
     p.heading_only = 1 if heading_only else 0
     p.w_smooth, p.w_length, p.w_ref = float(w_cost_smooth), float(w_cost_length), float(w_cost_ref)
     p.x_thre, p.y_thre = float(x_thre), float(y_thre)
     p.abstol, p.reltol, p.feastol, p.maxiters = float(abstol), float(reltol), float(feastol), int(maxiters)
+    p.diverge_factor = float(diverge_factor or 0.0)
     return p

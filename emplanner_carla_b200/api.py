@@ -20,7 +20,7 @@ PLAN_SLOTS = 4
 SCENE_HDR = 6
 
 DP_NO_OBSTACLE, DP_ALL_COLLIDE, DP_OVERFLOW = 1, 2, 4
-QP_OK, QP_UNKNOWN_MAXITER, QP_UNKNOWN_NUMERIC, QP_CORRIDOR_INDEX, QP_TOO_LARGE = 0, 1, 2, 4, 8
+QP_OK, QP_UNKNOWN_MAXITER, QP_UNKNOWN_NUMERIC, QP_UNKNOWN_DIVERGED, QP_CORRIDOR_INDEX, QP_TOO_LARGE = 0, 1, 2, 3, 4, 8
 ST_VALUE_ERROR, ST_INDEX_ERROR, ST_BAD_PROFILE = 0x10, 0x20, 0x40
 ST_COLS, ST_QP_POINTS, ST_DENSE = 16, 17, 401
 

@@ -154,11 +154,13 @@ extern "C" {
 void emp_smooth_params_default(EmpSmoothParams *p) {
     p->w_smooth = 0.4; p->w_length = 0.3; p->w_ref = 0.3; p->x_thre = 0.2; p->y_thre = 0.2;
     p->abstol = 1e-7; p->reltol = 1e-6; p->feastol = 1e-7; p->maxiters = 100; p->heading_only = 0;
+    p->diverge_factor = 2.0;
 }
 
 void emp_speed_qp_params_default(EmpSpeedQpParams *p) {
     p->w_s_dot2 = 10; p->w_v_ref = 50; p->w_jerk = 500; p->reference_speed = 50; p->max_lateral_accel = 0.2 * 9.8;
     p->abstol = 1e-7; p->reltol = 1e-6; p->feastol = 1e-7; p->maxiters = 100; p->reserved = 0;
+    p->diverge_factor = 2.0;
 }
 
 void emp_st_params_default(EmpStParams *p) {
@@ -179,6 +181,7 @@ void emp_qp_params_default(EmpQpParams *p) {
     p->obs_length = 5; p->obs_width = 5;
     p->abstol = 1e-7; p->reltol = 1e-6; p->feastol = 1e-7;
     p->maxiters = 100; p->reserved = 0;
+    p->diverge_factor = 2.0;
 }
 
 int emp_scene_stride(int kmax) { return EMP_SCENE_HDR + 2 * kmax; }
@@ -282,7 +285,11 @@ int emp_smooth_line_dev(const double *xy, const int32_t *npts, int max_points, i
     if (batch < 0 || max_points < 2) return fail(-2, "bad batch / max_points");
     if (batch == 0) return 0;
     if (!xy || !out || !status_iters) return fail(-1, "NULL argument");
-    emp::SmoothLaunch L{*p, batch, max_points, p->heading_only == 1 ? 1 : 0};
+    if (p->heading_only == 1) {                                        // cal_heading_kappa alone: any length
+        cudaError_t e = emp::launch_heading_kappa(xy, npts, out, status_iters, batch, max_points, (cudaStream_t)stream);
+        return e == cudaSuccess ? 0 : fail_cuda(e, "heading_kappa launch");
+    }
+    emp::SmoothLaunch L{*p, batch, max_points, 0};
     cudaError_t e = emp::launch_smooth(xy, npts, out, status_iters, L, (cudaStream_t)stream);
     return e == cudaSuccess ? 0 : fail_cuda(e, "smooth launch");
 }

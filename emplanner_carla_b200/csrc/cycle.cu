@@ -22,7 +22,7 @@ __global__ void cycle_path_points_kernel(const double *__restrict__ plans, int p
     const double *rec = plans + (size_t)f * plan_stride;
     const int NE = n_enr_max, NQ = (NE + 1) / 2;
     const int n = (int)rec[1];
-    const bool ok = (int)rec[3] == EMP_QP_OK || (int)rec[3] == EMP_QP_UNKNOWN_MAXITER || (int)rec[3] == EMP_QP_UNKNOWN_NUMERIC;
+    const bool ok = (int)rec[3] == EMP_QP_OK || (int)rec[3] == EMP_QP_UNKNOWN_MAXITER || (int)rec[3] == EMP_QP_UNKNOWN_NUMERIC || (int)rec[3] == EMP_QP_UNKNOWN_DIVERGED;
     const double *es = rec + PLAN_HDR, *ql = rec + PLAN_HDR + 2 * NE;
     double *o = xy + (size_t)f * max_points * 2;
     const int m = (ok && n >= 2 && n + 1 <= max_points && n <= NQ) ? n + 1 : 0;

@@ -488,7 +488,7 @@ EMP_LEVEL_UNROLL
         double rx[3] = {0.0, 0.0, 0.0}, ry[2] = {0.0, 0.0};
         EMP_UNROLL
         for (int r = 0; r < NR; ++r) { s[r] = 1.0; z[r] = 1.0; sm_ws[r * 32] = 0.0; sm_rz[r * 32] = 0.0; }
-        double resx0 = 1.0, resz0 = 1.0, gap_limit = 0.0;
+        double resx0 = 1.0, resz0 = 1.0, gap_min = 0.0;
         const double resy0 = 1.0;                                  // b = 0
         int it = -1;
         while (true) {
@@ -531,10 +531,11 @@ EMP_LEVEL_UNROLL
                 if (pres <= Q.feastol && dres <= Q.feastol && (gap <= Q.abstol || (have_rel && relgap <= Q.reltol))) break;
                 if (it == Q.maxiters) { qp_status = EMP_QP_UNKNOWN_MAXITER; break; }
                 if (!isfinite((gap + resx) + resz)) { qp_status = EMP_QP_UNKNOWN_NUMERIC; break; }
-                // Divergence exit: on an infeasible corridor coneqp has no certificate; cvxopt iterates until its
-                // Cholesky breaks down or maxiters and reports 'unknown'.  The gap of a converging solve never
-                // grows above its initial value, so a gap 100x the initial one ends the solve with 'unknown' too.
-                if (it > 0 && gap > gap_limit) { qp_status = EMP_QP_UNKNOWN_NUMERIC; break; }
+                // Divergence exit (include/emplanner.h, EmpQpParams.diverge_factor): on an infeasible corridor coneqp
+                // has no certificate; cvxopt iterates until its Cholesky breaks down or maxiters and reports 'unknown'.
+                // The gap of a converging solve decreases monotonically, so the first clear increase ends the solve.
+                if (it > 0 && Q.diverge_factor > 0.0 && gap > Q.diverge_factor * gap_min) { qp_status = EMP_QP_UNKNOWN_DIVERGED; break; }
+                gap_min = fmin(gap_min, gap);
             }
 
             {
@@ -647,7 +648,7 @@ EMP_LEVEL_UNROLL
                     }
                 }
                 gap = warp_sum(gs);
-                gap_limit = 100.0 * gap;
+                gap_min = gap;
             } else {
                 // step: recompute ds, dz of the corrector pass row by row (cheaper than keeping 28 registers)
                 double gdx[NR];

@@ -183,7 +183,7 @@ smooth_kernel(const double *__restrict__ xy_in, const int32_t *__restrict__ npts
             EMP_UNROLL
             for (int q = 0; q < 2; ++q) { s[c][q][0] = s[c][q][1] = 1.0; z[c][q][0] = z[c][q][1] = 1.0; }
         auto hrow = [&](int c, int q, int b) -> double { return b == 0 ? ref[c][q] + thr[c] : -(ref[c][q] - thr[c]); };
-        double gap = 0.0, resx0 = 1.0, resz0 = 1.0, gap_limit = 0.0;
+        double gap = 0.0, resx0 = 1.0, resz0 = 1.0, gap_min = 0.0;
         double rx[2][2] = {{0, 0}, {0, 0}}, rz[2][2][2], ws3[2][2][2];
         EMP_UNROLL
         for (int c = 0; c < 2; ++c)
@@ -228,7 +228,8 @@ smooth_kernel(const double *__restrict__ xy_in, const int32_t *__restrict__ npts
                 if (pres <= Q.feastol && dres <= Q.feastol && (gap <= Q.abstol || (have_rel && relgap <= Q.reltol))) break;
                 if (it == Q.maxiters) { status = EMP_QP_UNKNOWN_MAXITER; break; }
                 if (!isfinite((gap + resx) + resz)) { status = EMP_QP_UNKNOWN_NUMERIC; break; }
-                if (it > 0 && gap > gap_limit) { status = EMP_QP_UNKNOWN_NUMERIC; break; }
+                if (it > 0 && Q.diverge_factor > 0.0 && gap > Q.diverge_factor * gap_min) { status = EMP_QP_UNKNOWN_DIVERGED; break; }
+                gap_min = fmin(gap_min, gap);
             }
             // factor S = H + diag(z/s summed over a variable's two rows), both coordinates
             Fac2 F[2];
@@ -357,7 +358,7 @@ smooth_kernel(const double *__restrict__ xy_in, const int32_t *__restrict__ npts
                                 gs += s[c][q][b] * z[c][q][b];
                             }
                 gap = warp_sum(gs);
-                gap_limit = 100.0 * gap;
+                gap_min = gap;
             } else {
                 double gs = 0.0;
                 EMP_UNROLL
@@ -419,7 +420,58 @@ smooth_kernel(const double *__restrict__ xy_in, const int32_t *__restrict__ npts
     }
 }
 
+// cal_heading_kappa (planning_utils.py:185-228) for polylines of any length: one thread per point.  theta_i needs the
+// points i-1..i+1, kappa_i the thetas i-1..i+1, so a thread reads at most 5 points and evaluates up to 3 arctangents;
+// same expressions as the tail of smooth_kernel, so both give the same bits.
+__global__ void heading_kappa_kernel(const double *__restrict__ xy_in, const int32_t *__restrict__ npts,
+                                     double *__restrict__ out, int32_t *__restrict__ status_iters, int batch,
+                                     int max_points) {
+    const int line = blockIdx.y;
+    const int n = npts ? min(npts[line], max_points) : max_points;
+    const double *xy = xy_in + (size_t)line * max_points * 2;
+    double *o = out + (size_t)line * max_points * 4;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < max_points; i += gridDim.x * blockDim.x) {
+        if (i == 0) {
+            status_iters[2 * line] = n < 2 ? EMP_QP_TOO_LARGE : 0;
+            status_iters[2 * line + 1] = 0;
+        }
+        if (i >= n || n < 2) continue;
+        auto theta_at = [&](int j, double &ddx, double &ddy) -> double {
+            const int a = max(j - 1, 0), b = min(j, n - 2);              // dx_pre = dx_[j-1], dx_aft = dx_[j] (clamped)
+            ddx = ((xy[2 * (a + 1)] - xy[2 * a]) + (xy[2 * (b + 1)] - xy[2 * b])) / 2;
+            ddy = ((xy[2 * (a + 1) + 1] - xy[2 * a + 1]) + (xy[2 * (b + 1) + 1] - xy[2 * b + 1])) / 2;
+            return atan2(ddy, ddx);
+        };
+        double dx, dy, tx, ty;
+        const double th = theta_at(i, dx, dy);
+        const int a = max(i - 1, 0), b = min(i, n - 2);
+        const double th_a = a == i ? th : theta_at(a, tx, ty);
+        const double th_a1 = a + 1 == i ? th : theta_at(a + 1, tx, ty);
+        const double th_b = b == i ? th : (b == a ? th_a : theta_at(b, tx, ty));
+        const double th_b1 = b + 1 == i ? th : (b + 1 == a + 1 ? th_a1 : theta_at(b + 1, tx, ty));
+        const double dth = ((th_a1 - th_a) + (th_b1 - th_b)) / 2;
+        o[4 * i] = xy[2 * i];
+        o[4 * i + 1] = xy[2 * i + 1];
+        o[4 * i + 2] = th;
+        o[4 * i + 3] = sin(dth) / sqrt(dx * dx + dy * dy);
+    }
+}
+
 }  // namespace
+
+cudaError_t launch_heading_kappa(const double *xy, const int32_t *npts, double *out, int32_t *status_iters, int batch,
+                                 int max_points, cudaStream_t st) {
+    const int threads = 128;
+    int gx = (max_points + threads - 1) / threads;
+    if (gx > 1024) gx = 1024;
+    for (int b0 = 0; b0 < batch; b0 += 65535) {                        // gridDim.y limit
+        const int nb = batch - b0 < 65535 ? batch - b0 : 65535;
+        heading_kappa_kernel<<<dim3(gx, nb), threads, 0, st>>>(xy + (size_t)b0 * max_points * 2, npts ? npts + b0 : nullptr,
+                                                              out + (size_t)b0 * max_points * 4, status_iters + 2 * (size_t)b0,
+                                                              nb, max_points);
+    }
+    return cudaGetLastError();
+}
 
 cudaError_t launch_smooth(const double *xy, const int32_t *npts, double *out, int32_t *status_iters,
                           const SmoothLaunch &p, cudaStream_t st) {

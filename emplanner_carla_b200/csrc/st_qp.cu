@@ -306,7 +306,7 @@ speed_qp_kernel(const double *__restrict__ start, const double *__restrict__ st_
     double s[5], z[5], w[5], g[5];
     EMP_UNROLL
     for (int r = 0; r < 5; ++r) { w[r] = 1.0; s[r] = 1.0; z[r] = 1.0; }
-    double yv = 0.0, gap = 0.0, resx0 = 1.0, resz0 = 1.0, gap_limit = 0.0;
+    double yv = 0.0, gap = 0.0, resx0 = 1.0, resz0 = 1.0, gap_min = 0.0;
     if (factor(w)) {
         status = EMP_QP_UNKNOWN_NUMERIC;                               // cvxopt: ValueError("Rank(A) < p or ...")
     } else {
@@ -351,7 +351,7 @@ speed_qp_kernel(const double *__restrict__ start, const double *__restrict__ st_
                 gs += s[r] * z[r];
             }
         gap = warp_sum(gs);
-        gap_limit = 100.0 * gap;
+        gap_min = gap;
 
         // ---- interior-point iterations --------------------------------------------------------------
         double rxv[2], rz[5], ws3[5], tq[5], dsv[5], dz[5];
@@ -399,7 +399,8 @@ speed_qp_kernel(const double *__restrict__ start, const double *__restrict__ st_
             if (pres <= Q.feastol && dres <= Q.feastol && (gap <= Q.abstol || (have_rel && relgap <= Q.reltol))) break;
             if (it == Q.maxiters) { status = EMP_QP_UNKNOWN_MAXITER; break; }
             if (!isfinite((gap + resx) + resz)) { status = EMP_QP_UNKNOWN_NUMERIC; break; }
-            if (it > 0 && gap > gap_limit) { status = EMP_QP_UNKNOWN_NUMERIC; break; }
+            if (it > 0 && Q.diverge_factor > 0.0 && gap > Q.diverge_factor * gap_min) { status = EMP_QP_UNKNOWN_DIVERGED; break; }
+            gap_min = fmin(gap_min, gap);
 
             double is[5];
             EMP_UNROLL

@@ -2,9 +2,11 @@
 
 The Cartesian<->Frenet arithmetic runs in libemplanner.so (csrc/frenet.cu) through
 emplanner_carla_b200.api.HostPlanner; `sampling` is pure list slicing and stays in Python.
-Reference line numbers cite planning_utils.py @ 1f115a5.  Not provided: the three CARLA-actor helpers
-(Vector_fun, waypoint_list_2_target_path, predict_block*), which need live simulator actors.
+Reference line numbers cite planning_utils.py @ 1f115a5.  The three CARLA-actor helpers (Vector_fun,
+waypoint_list_2_target_path, predict_block) are accessor code around simulator objects: they are duck-typed here
+(anything with .x/.y/.z, .transform.location, .get_location() ... works; `carla` itself is never imported).
 """
+import math
 import numpy as np
 
 from emplanner_carla_b200 import api, _lib
@@ -20,6 +22,38 @@ def _line(path):
 
 def _pts(xy_list):
     return np.asarray([(p[0], p[1]) for p in xy_list], dtype=np.float64)[None]
+
+
+def Vector_fun(loc_1, loc_2):
+    """Unit vector from loc_1 to loc_2, rounded to 4 decimals (reference :14-26; used by global_planning.py:132
+    while it builds the route graph).  Three subtractions and a norm on simulator objects: host code."""
+    d = [loc_2.x - loc_1.x, loc_2.y - loc_1.y, loc_2.z - loc_1.z]
+    norm = np.linalg.norm(d) + np.finfo(float).eps
+    return np.round([d[0] / norm, d[1] / norm, d[2] / norm], 4)
+
+
+def waypoint_list_2_target_path(pathway):
+    """[(waypoint, road_option), ...] -> [(x, y, theta, kappa), ...] (reference :29-46); heading and curvature
+    of the whole route come from cal_heading_kappa on the GPU."""
+    xy = [(w[0].transform.location.x, w[0].transform.location.y) for w in pathway]
+    theta, kappa = cal_heading_kappa(xy)
+    return [(xy[i][0], xy[i][1], theta[i], kappa[i]) for i in range(len(theta))]
+
+
+def predict_block(ego_vehicle, ts=0.1):
+    """Ego pose one prediction horizon ahead from its velocity, side-slip and yaw rate (reference :591-614).
+    Returns (x, y, yaw).  A dozen scalar operations on actor accessors, once per plan: host code."""
+    loc = ego_vehicle.get_location()
+    yaw = ego_vehicle.get_transform().rotation.yaw * (math.pi / 180)
+    vel = ego_vehicle.get_velocity()
+    speed = math.sqrt(vel.x * vel.x + vel.y * vel.y + vel.z * vel.z)
+    slip = math.atan2(vel.y, vel.x) - yaw                     # angle between velocity and body axis
+    v_lat = speed * math.sin(slip)
+    v_lon = speed * math.cos(slip)
+    x = loc.x + v_lon * ts * math.cos(yaw) - v_lat * ts * math.sin(yaw)
+    y = loc.y + v_lat * ts * math.cos(yaw) + v_lon * ts * math.sin(yaw)
+    yaw_rate = ego_vehicle.get_angular_velocity().z * (math.pi / 180)
+    return x, y, yaw + yaw_rate * ts
 
 
 def match_projection_points(xy_list: list, frenet_path_node_list: list):
@@ -107,8 +141,8 @@ def cal_heading_kappa(frenet_path_xy_list: list):
     """Heading and curvature of a polyline by central differences (reference :185-228).
     Returns (theta list, kappa list)."""
     n = len(frenet_path_xy_list)
-    if n < 2 or n > 64:
-        raise NotImplementedError("cal_heading_kappa on the GPU handles 2..64 points (got %d)" % n)
+    if n < 2:
+        raise IndexError("list index out of range")            # the reference indexes dx_[0] of an empty list (:213)
     sp = api.smooth_params(heading_only=True)
     out, _, _ = _runtime.planner().smooth_lines(_pts(frenet_path_xy_list), sp)
     return list(out[0, :, 2]), list(out[0, :, 3])
@@ -189,7 +223,6 @@ def cal_proj_point_1(s, pre_match_index, frenet_path_opt: list, s_map: list):
 def predict_block_based_on_frenet(vehicle_loc, vehicle_velocity, local_frenet_path_opt, cur_path_s, cur_path_l, ts=0.1):
     """Ego position one planning period ahead, along the current path (reference :617-644).  vehicle_loc /
     vehicle_velocity only need .x/.y(/.z) attributes (carla.Location / carla.Vector3D in the reference)."""
-    import math
     speed = math.sqrt(vehicle_velocity.x * vehicle_velocity.x + vehicle_velocity.y * vehicle_velocity.y +
                       vehicle_velocity.z * vehicle_velocity.z)
     s_map = cal_s_map_fun(local_frenet_path_opt, origin_xy=(vehicle_loc.x, vehicle_loc.y))

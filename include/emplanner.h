@@ -50,6 +50,7 @@ extern "C" {
 #define EMP_QP_OK               0     /* 'optimal' */
 #define EMP_QP_UNKNOWN_MAXITER  1     /* cvxopt status 'unknown' after maxiters */
 #define EMP_QP_UNKNOWN_NUMERIC  2     /* 'unknown': factorisation breakdown / non-finite iterate */
+#define EMP_QP_UNKNOWN_DIVERGED 3     /* 'unknown': duality gap grew above diverge_factor x its smallest earlier value */
 #define EMP_QP_CORRIDOR_INDEX   4     /* cal_lmin_lmax would raise IndexError, path_planning.py:265-272 */
 #define EMP_QP_TOO_LARGE        8     /* more than EMP_MAX_QP_POINTS stations, or fewer than 2 */
 #define EMP_ST_VALUE_ERROR      0x10  /* the reference raises ValueError (scipy interp1d out of range, empty table) */
@@ -78,7 +79,18 @@ typedef struct EmpQpParams {          /* Quadratic_planning :78-81, cal_lmin_lma
     double abstol, reltol, feastol;   /* 1e-7, 1e-6, 1e-7 */
     int32_t maxiters;                 /* 100 */
     int32_t reserved;
+    double diverge_factor;            /* 2: see "divergence exit" below; 0 = iterate like cvxopt until breakdown */
 } EmpQpParams;
+
+/* Divergence exit (all three QP kernels).  cvxopt's coneqp has no infeasibility certificate: on an infeasible
+ * problem (empty corridor) it iterates until its Cholesky factorisation breaks down or maxiters and returns
+ * status 'unknown' with whatever iterate it has; the reference never looks at the status (path_planning.py:211-219).
+ * Those last iterates are not a numerically well defined function of the input (two exact-arithmetic-equivalent
+ * factorisations differ by O(1 m), profiles/parity_r2.json).  With diverge_factor > 0 a solve ends with
+ * EMP_QP_UNKNOWN_DIVERGED as soon as the duality gap exceeds diverge_factor x the smallest gap of the earlier
+ * iterations - the last iterate both sides still agree on to < 1e-6 m.  The gap of a converging solve decreases
+ * monotonically (worst ratio 0.98 over 3349 optimal frames), so 'optimal' frames are untouched.  oracle/coneqp.py
+ * implements the same rule behind the same parameter. */
 
 typedef struct EmpStParams {          /* speed_DP, speed_planning_test.py:101-102 */
     double reference_speed;           /* 50 */
@@ -93,6 +105,7 @@ typedef struct EmpSmoothParams {      /* smooth_reference_line, planning_utils.p
     double abstol, reltol, feastol;   /* 1e-7, 1e-6, 1e-7 */
     int32_t maxiters;                 /* 100 */
     int32_t heading_only;             /* 1: skip the QP, output cal_heading_kappa (:185-228) of the input polyline */
+    double diverge_factor;            /* 2, as in EmpQpParams */
 } EmpSmoothParams;
 
 typedef struct EmpSpeedQpParams {     /* speed_QP :403-404, generate_convex_space :309, cvxopt defaults */
@@ -102,6 +115,7 @@ typedef struct EmpSpeedQpParams {     /* speed_QP :403-404, generate_convex_spac
     double abstol, reltol, feastol;   /* 1e-7, 1e-6, 1e-7 */
     int32_t maxiters;                 /* 100 */
     int32_t reserved;
+    double diverge_factor;            /* 2, as in EmpQpParams */
 } EmpSpeedQpParams;
 
 void emp_speed_qp_params_default(EmpSpeedQpParams *p);

@@ -61,8 +61,17 @@ class _Chol2:
 
 
 def qp(P, q, G, h, A=None, b=None, maxiters=MAXITERS, abstol=ABSTOL, reltol=RELTOL,
-       feastol=FEASTOL, trace=None, kkt=None):
-    """Returns dict(x, y, s, z, status, iterations, gap, pcost, dcost, pres, dres)."""
+       feastol=FEASTOL, trace=None, kkt=None, diverge_factor=None):
+    """Returns dict(x, y, s, z, status, iterations, gap, pcost, dcost, pres, dres).
+
+    diverge_factor (None/0 = cvxopt behaviour): documented early exit of the GPU kernels
+    (EmpQpParams.diverge_factor, csrc/sl_qp.cu): a duality gap above diverge_factor x the
+    smallest gap of the earlier iterations ends the solve with status 'unknown' and the current
+    iterate.  coneqp has no infeasibility certificate: on an infeasible problem cvxopt goes on for
+    a few more iterations until its Cholesky breaks down (status 'unknown' as well), through
+    iterates that are no longer a numerically well defined function of the input (two exact-
+    arithmetic-equivalent factorisations differ by O(1 m) there, profiles/parity_r2.json); the
+    gap of a converging solve decreases monotonically (worst ratio seen: tests/test_qp_parity)."""
     P = np.asarray(P, dtype=np.float64)
     n = P.shape[0]
     q = np.asarray(q, dtype=np.float64).reshape(-1)
@@ -95,6 +104,7 @@ def qp(P, q, G, h, A=None, b=None, maxiters=MAXITERS, abstol=ABSTOL, reltol=RELT
     if tz >= -1e-8 * max(nrmz, 1.0):
         z = z + (1.0 + tz)
     gap = s @ z
+    gap_min = gap
 
     def result(status, it):
         return dict(x=x, y=y, s=s, z=z, status=status, iterations=it, gap=gap,
@@ -128,6 +138,9 @@ def qp(P, q, G, h, A=None, b=None, maxiters=MAXITERS, abstol=ABSTOL, reltol=RELT
             return result("unknown", it)
         if not (np.isfinite(gap) and np.isfinite(resx) and np.isfinite(resz)):
             return result("unknown", it)
+        if diverge_factor and it > 0 and gap > diverge_factor * gap_min:
+            return result("unknown", it)
+        gap_min = min(gap_min, gap)
 
         if it == 0:
             d = np.sqrt(s / z)                      # misc.compute_scaling

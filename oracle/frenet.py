@@ -181,9 +181,9 @@ def smooth_matrices(xy, w_smooth=0.4, w_length=0.3, w_ref=0.3, x_thre=0.2, y_thr
     return P, q, G, h
 
 
-def smooth_reference_line(xy, **kw):
+def smooth_reference_line(xy, diverge_factor=None, **kw):
     P, q, G, h = smooth_matrices(xy, **kw)
-    res = coneqp.qp(P, q, G, h)
+    res = coneqp.qp(P, q, G, h, diverge_factor=diverge_factor)
     x = res["x"]
     pts = [(x[i], x[i + 1]) for i in range(0, len(x), 2)]
     th, k = heading_kappa(pts)

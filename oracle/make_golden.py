@@ -32,8 +32,60 @@ def _quiet(fn, *a, **kw):
         return fn(*a, **kw)
 
 
-def make_sl(tag, lattice, config_id, batch, extra=None):
+DIVERGE_FACTOR = 2.0          # default of EmpQpParams.diverge_factor (include/emplanner.h)
+_STATUS_CODE = {"optimal": 0}
+
+
+def _sl_frame(job):
+    """One golden frame: reference DP -> [::2] -> reference corridor -> reference Quadratic_planning (matrices by the
+    unmodified reference, solve by oracle/coneqp.py through the cvxopt shim), then the same QP once more with the
+    kernels' divergence exit."""
+    from oracle import sl_qp, coneqp
+    sc, b, kw = job
     pp, pu, _ = refshim.modules()
+    K = int(sc["nobs"][b])
+    os_, ol_ = list(sc["obs_s"][b, :K]), list(sc["obs_l"][b, :K])
+    st = (sc["s0"][b], sc["l0"][b], sc["dl0"][b], sc["ddl0"][b])
+    r = dict(b=b)
+    t0 = time.perf_counter()
+    rs, rl = _quiet(pp.DP_algorithm, list(os_), list(ol_), *st, **kw)
+    r["ref_dp_seconds"] = time.perf_counter() - t0
+    rs = np.array(rs, dtype=np.float64)
+    rl = np.array(rl, dtype=np.float64).reshape(-1)
+    s_i, l_i, rows_i = sl_dp.dp_algorithm(os_, ol_, *st, mode="inv", **kw)
+    assert np.array_equal(rs, s_i) and np.array_equal(rl, l_i), "oracle(inv) != reference at frame %d" % b
+    s_c, l_c, rows_c = sl_dp.dp_algorithm(os_, ol_, *st, mode="closed", **kw)
+    r.update(ref_s=rs, ref_l=rl, rows=rows_i, closed_rows_equal=int(np.array_equal(rows_i, rows_c)),
+             closed_n_equal=int(len(s_c) == len(rs)),
+             closed_dl=float(np.abs(l_c - rl).max()) if len(s_c) == len(rs) else np.nan)
+    ds_, dl_ = rs[::2], rl[::2]
+    try:
+        lmin, lmax = pp.cal_lmin_lmax(ds_, dl_, os_, ol_, 5, 5)
+    except IndexError:
+        r["cor_index_error"] = 1
+        return r
+    r["cor_index_error"] = 0
+    r["lmin"], r["lmax"] = np.array(lmin), np.array(lmax)
+    refshim.qp_log_enabled = True
+    refshim.qp_log.clear()
+    ql, qdl, qddl = pp.Quadratic_planning(lmin, lmax, st[1], st[2], st[3])
+    log = refshim.qp_log[-1]
+    res = log["result"]
+    r.update(qp_l=np.array(ql), qp_dl=np.array(qdl), qp_ddl=np.array(qddl), qp_optimal=int(res["status"] == "optimal"),
+             qp_iters=res["iterations"])
+    tr = []
+    rd = coneqp.qp(log["P"], log["q"], log["G"], log["h"], log["A"], log["b"], diverge_factor=DIVERGE_FACTOR, trace=tr)
+    x = rd["x"]
+    gaps = np.array([t["gap"] for t in tr])
+    r.update(qpd_l=x[0::3].copy(), qpd_dl=x[1::3].copy(), qpd_ddl=x[2::3].copy(), qpd_iters=rd["iterations"],
+             qpd_optimal=int(rd["status"] == "optimal"),
+             gap_ratio_max=float(max(gaps[k] / gaps[:k].min() for k in range(1, len(gaps)))) if len(gaps) > 1 else 0.0)
+    return r
+
+
+def make_sl(tag, lattice, config_id, batch, extra=None, procs=None):
+    import multiprocessing as mp
+    refshim.modules()
     sc = scenes.sl_scenes(batch, lattice, config_id)
     if extra is not None:                                   # prepend hand-written frames
         for k in sc:
@@ -41,54 +93,46 @@ def make_sl(tag, lattice, config_id, batch, extra=None):
     B = len(sc["s0"])
     nmax = sl_dp.max_enriched(lattice.col, lattice.sample_s, lattice.sampling_res)
     nq = (nmax + 1) // 2
+    nanq = lambda: np.full((B, nq), np.nan)
     out = dict(ref_n=np.zeros(B, np.int32), ref_s=np.full((B, nmax), np.nan), ref_l=np.full((B, nmax), np.nan),
                rows=np.zeros((B, lattice.col), np.int32), cor_index_error=np.zeros(B, np.int32),
-               ref_lmin=np.full((B, nq), np.nan), ref_lmax=np.full((B, nq), np.nan),
-               qp_l=np.full((B, nq), np.nan), qp_dl=np.full((B, nq), np.nan), qp_ddl=np.full((B, nq), np.nan),
-               qp_optimal=np.zeros(B, np.int32), qp_iters=np.zeros(B, np.int32), ref_dp_seconds=np.zeros(B))
+               ref_lmin=nanq(), ref_lmax=nanq(), qp_l=nanq(), qp_dl=nanq(), qp_ddl=nanq(),
+               qp_optimal=np.zeros(B, np.int32), qp_iters=np.zeros(B, np.int32),
+               qpd_l=nanq(), qpd_dl=nanq(), qpd_ddl=nanq(), qpd_optimal=np.zeros(B, np.int32),
+               qpd_iters=np.zeros(B, np.int32), gap_ratio_max=np.zeros(B), ref_dp_seconds=np.zeros(B),
+               closed_rows_equal=np.zeros(B, np.int32), closed_n_equal=np.zeros(B, np.int32), closed_dl=np.zeros(B))
     kw = lattice.kwargs()
-    refshim.qp_log_enabled = True
-    for b in range(B):
-        K = int(sc["nobs"][b])
-        os_, ol_ = list(sc["obs_s"][b, :K]), list(sc["obs_l"][b, :K])
-        st = (sc["s0"][b], sc["l0"][b], sc["dl0"][b], sc["ddl0"][b])
-        t0 = time.perf_counter()
-        rs, rl = _quiet(pp.DP_algorithm, list(os_), list(ol_), *st, **kw)
-        out["ref_dp_seconds"][b] = time.perf_counter() - t0
-        rs = np.array(rs, dtype=np.float64)
-        rl = np.array(rl, dtype=np.float64).reshape(-1)
-        s_i, l_i, rows_i = sl_dp.dp_algorithm(os_, ol_, *st, mode="inv", **kw)
-        assert np.array_equal(rs, s_i) and np.array_equal(rl, l_i), "oracle(inv) != reference at frame %d" % b
-        n = len(rs)
-        out["ref_n"][b] = n
-        out["ref_s"][b, :n] = rs
-        out["ref_l"][b, :n] = rl
-        out["rows"][b] = rows_i
-        ds_, dl_ = rs[::2], rl[::2]
-        try:
-            lmin, lmax = pp.cal_lmin_lmax(ds_, dl_, os_, ol_, 5, 5)
-        except IndexError:
-            out["cor_index_error"][b] = 1
-            continue
-        m = len(lmin)
-        out["ref_lmin"][b, :m] = lmin
-        out["ref_lmax"][b, :m] = lmax
-        refshim.qp_log.clear()
-        ql, qdl, qddl = pp.Quadratic_planning(lmin, lmax, st[1], st[2], st[3])
-        res = refshim.qp_log[-1]["result"]
-        out["qp_l"][b, :m] = ql
-        out["qp_dl"][b, :m] = qdl
-        out["qp_ddl"][b, :m] = qddl
-        out["qp_optimal"][b] = int(res["status"] == "optimal")
-        out["qp_iters"][b] = res["iterations"]
-        if b % 16 == 0:
-            print(tag, b, "/", B, flush=True)
+    procs = procs or len(os.sched_getaffinity(0))
+    with mp.get_context("fork").Pool(procs) as pool:
+        for i, r in enumerate(pool.imap_unordered(_sl_frame, [(sc, b, kw) for b in range(B)], chunksize=4)):
+            b = r["b"]
+            n = len(r["ref_s"])
+            out["ref_n"][b] = n
+            out["ref_s"][b, :n] = r["ref_s"]
+            out["ref_l"][b, :n] = r["ref_l"]
+            for k in ("rows", "ref_dp_seconds", "closed_rows_equal", "closed_n_equal", "closed_dl", "cor_index_error"):
+                out[k][b] = r[k]
+            if not r["cor_index_error"]:
+                m = len(r["lmin"])
+                out["ref_lmin"][b, :m], out["ref_lmax"][b, :m] = r["lmin"], r["lmax"]
+                for k in ("qp_l", "qp_dl", "qp_ddl", "qpd_l", "qpd_dl", "qpd_ddl"):
+                    out[k][b, :m] = r[k]
+                for k in ("qp_optimal", "qp_iters", "qpd_optimal", "qpd_iters", "gap_ratio_max"):
+                    out[k][b] = r[k]
+            if i % 64 == 0:
+                print(tag, i, "/", B, flush=True)
     meta = dict(ref_commit=REF_COMMIT, lattice=np.array([lattice.row, lattice.col, lattice.sample_s, lattice.sample_l,
                                                           lattice.sampling_res], dtype=np.float64),
-                config_id=config_id, numpy=np.__version__)
+                config_id=config_id, numpy=np.__version__, diverge_factor=DIVERGE_FACTOR)
     np.savez_compressed(os.path.join(GOLDEN, "sl_%s.npz" % tag), **sc, **out, **meta)
+    ok = out["cor_index_error"] == 0
     print(tag, "done: optimal", int(out["qp_optimal"].sum()), "/", B, "index errors", int(out["cor_index_error"].sum()),
-          "mean ref DP s/frame %.3f" % out["ref_dp_seconds"].mean())
+          "mean ref DP s/frame %.3f" % out["ref_dp_seconds"].mean(),
+          "closed-form vs reference: row flips %d, length flips %d, worst |dl| %.3e" % (
+              int((out["closed_rows_equal"] == 0).sum()), int((out["closed_n_equal"] == 0).sum()),
+              float(np.nanmax(out["closed_dl"]))),
+          "optimal disagreement with/without divergence exit:", int((out["qp_optimal"] != out["qpd_optimal"])[ok].sum()),
+          "worst gap ratio on optimal frames %.4f" % float(out["gap_ratio_max"][ok & (out["qp_optimal"] == 1)].max()))
 
 
 def make_frenet():
@@ -354,23 +398,117 @@ def make_speed_stub():
     print("speed_stub done:", exc)
 
 
+def motion_planning_messages(n_frames=40):
+    """Recorded inputs of test_9.motion_planning (the tuple the main loop sends, test_9.py:390-392) for an ego car
+    driving along the synthetic global route: static obstacles ahead (some frames none, some beyond the 30 m gate of
+    test_9.py:116), a slower dynamic obstacle on every 4th frame (test_9.py:137-169)."""
+    _, pu, _ = refshim.modules()
+    xy = scenes.reference_line()
+    th, k = pu.cal_heading_kappa([tuple(p) for p in xy])
+    route = [(float(xy[i, 0]), float(xy[i, 1]), float(th[i]), float(k[i])) for i in range(len(xy))]
+    rng = np.random.default_rng(scenes.BASE_SEED + 900)
+    on_route = lambda x, off: (float(x), float(8 * np.sin(x / 60) + off))
+    msgs = []
+    x0 = 60.0
+    first_match, _ = pu.find_match_points([on_route(x0, 0.0)], route, True, 0)
+    match = list(first_match)
+    for f in range(n_frames):
+        x = x0 + 6.5 * f
+        ego = on_route(x, rng.uniform(-0.4, 0.4))
+        heading = float(np.arctan2(8 / 60 * np.cos(x / 60), 1.0))
+        speed = rng.uniform(7.0, 12.0)
+        v = (float(speed * np.cos(heading) + rng.uniform(-0.2, 0.2)), float(speed * np.sin(heading) + rng.uniform(-0.2, 0.2)))
+        a = (float(rng.uniform(-1, 1)), float(rng.uniform(-0.5, 0.5)))
+        pred = (ego[0] + v[0] * 0.2, ego[1] + v[1] * 0.2)
+        K = int(rng.integers(0, 4))
+        far = f % 9 == 5                                      # nearest obstacle beyond 30 m: the list is ignored
+        stat = []
+        for d in np.sort(rng.uniform(31.0, 40.0, K) if far else rng.uniform(10.0, 28.0, K)):
+            ox, oy = on_route(x + d, rng.uniform(-3.0, 3.0))
+            stat.append((ox, oy, float(np.hypot(ox - ego[0], oy - ego[1]))))
+        stat.sort(key=lambda t: t[2])
+        dyn = []
+        if f % 4 == 2:
+            gap = float(rng.uniform(18.0, 30.0))
+            ox, oy = on_route(x + gap, 0.0)
+            dyn.append((ox, oy, gap, float(rng.uniform(2.0, 5.0))))
+        msgs.append((stat, dyn, ego, pred, v, a, route, list(match)))
+    return msgs
+
+
+def make_motion_planning(n_frames=40):
+    """Replay the UNMODIFIED source text of test_9.motion_planning (test_9.py:92-221) against a fake Pipe on the
+    reference's own planner modules and store every conn.send payload.  Two runs: with the cvxopt shim behaving like
+    cvxopt (`ref_*`), and with the kernels' documented divergence exit (`refd_*`); they differ only on frames whose
+    path QP ends 'unknown' (infeasible corridor), where the former is not numerically reproducible."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import motion_planning_caller as mpc
+    pp, pu, _ = refshim.modules()
+    text = mpc.reference_function_text()
+    msgs = motion_planning_messages(n_frames)
+    F = len(msgs)
+    rec = dict(route=np.array(msgs[0][6]), first_match=np.array(msgs[0][7], np.int32),
+               ego=np.array([m[2] for m in msgs]), pred=np.array([m[3] for m in msgs]),
+               vel=np.array([m[4] for m in msgs]), acc=np.array([m[5] for m in msgs]),
+               n_static=np.array([len(m[0]) for m in msgs], np.int32), static=np.full((F, 3, 3), np.nan),
+               n_dynamic=np.array([len(m[1]) for m in msgs], np.int32), dynamic=np.full((F, 1, 4), np.nan))
+    for f, m in enumerate(msgs):
+        for j, o in enumerate(m[0]):
+            rec["static"][f, j] = o
+        for j, o in enumerate(m[1]):
+            rec["dynamic"][f, j] = o
+    import hashlib
+    rec["caller_sha256"] = hashlib.sha256(text.encode()).hexdigest()
+    for tag, df in (("ref", None), ("refd", DIVERGE_FACTOR)):
+        refshim.diverge_factor = df
+        refshim.qp_log_enabled = True
+        refshim.qp_log.clear()
+        sent = _quiet(mpc.replay, text, pu, pp, msgs)
+        refshim.diverge_factor = None
+        assert len(sent) == F and len(refshim.qp_log) == 3 * F
+        rec[tag + "_cart"] = np.full((F, 28, 4), np.nan)
+        rec[tag + "_cart_n"] = np.zeros(F, np.int32)
+        rec[tag + "_path_s"] = np.full((F, 27), np.nan)
+        rec[tag + "_path_l"] = np.full((F, 27), np.nan)
+        rec[tag + "_path_n"] = np.zeros(F, np.int32)
+        rec[tag + "_match"] = np.zeros(F, np.int32)
+        rec[tag + "_qp_status"] = np.zeros((F, 3), np.int32)   # 1 = optimal, for the frame's QP#1, QP#2, QP#3
+        rec[tag + "_qp_iters"] = np.zeros((F, 3), np.int32)
+        for f, (cart, match, ps, pl) in enumerate(sent):
+            rec[tag + "_cart_n"][f] = len(cart)
+            rec[tag + "_cart"][f, :len(cart)] = np.array(cart)
+            rec[tag + "_path_n"][f] = len(ps)
+            rec[tag + "_path_s"][f, :len(ps)] = ps
+            rec[tag + "_path_l"][f, :len(pl)] = np.array(pl, dtype=np.float64).reshape(-1)
+            rec[tag + "_match"][f] = match[0]
+            for q in range(3):
+                r = refshim.qp_log[3 * f + q]["result"]
+                rec[tag + "_qp_status"][f, q] = int(r["status"] == "optimal")
+                rec[tag + "_qp_iters"][f, q] = r["iterations"]
+    np.savez_compressed(os.path.join(GOLDEN, "motion_planning.npz"), ref_commit=REF_COMMIT, **rec)
+    unk = (rec["ref_qp_status"][:, 1] == 0)
+    same = [f for f in range(F) if np.array_equal(rec["ref_cart"][f], rec["refd_cart"][f], equal_nan=True)]
+    print("motion_planning done: %d frames, path QP 'unknown' on %d, payload identical with/without the divergence exit on %d"
+          % (F, int(unk.sum()), len(same)))
+
+
 def _rng_a0(n):
     return np.random.default_rng(scenes.BASE_SEED + 300).uniform(-1.0, 1.0, n)
 
 
 def main(argv):
-    what = argv or ["A", "B", "C", "frenet", "st", "st_misc", "st_back", "speed_stub"]
+    what = argv or ["A", "B", "C", "frenet", "st", "st_misc", "st_back", "speed_stub", "motion_planning"]
     os.makedirs(GOLDEN, exist_ok=True)
     if "A" in what:
-        make_sl("A", scenes.LATTICE_A, 0, 192)
+        make_sl("A", scenes.LATTICE_A, 0, 512)
     if "B" in what:
         # frame 0 = BASELINE.json configs[0]: single ego frame, 60x9 lattice, 3 static obstacles
         nanpad = lambda v: np.array([v + [np.nan] * (scenes.KMAX - len(v))])
         extra = dict(obs_s=nanpad([22.0, 47.0, 71.0]), obs_l=nanpad([0.6, -1.2, 1.8]), nobs=np.array([3], np.int32),
                      s0=np.array([0.5]), l0=np.array([0.1]), dl0=np.array([0.01]), ddl0=np.array([0.0]))
-        make_sl("B", scenes.LATTICE_B, 1, 15, extra=extra)
+        make_sl("B", scenes.LATTICE_B, 1, 127, extra=extra)
     if "C" in what:
-        make_sl("C", scenes.LATTICE_C, 2, 96)
+        make_sl("C", scenes.LATTICE_C, 2, 1024)
     if "frenet" in what:
         make_frenet()
     if "st" in what:
@@ -381,6 +519,8 @@ def main(argv):
         make_st_back()
     if "speed_stub" in what:
         make_speed_stub()
+    if "motion_planning" in what:
+        make_motion_planning()
 
 
 if __name__ == "__main__":

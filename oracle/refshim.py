@@ -60,6 +60,7 @@ _installed = False
 _mods = None
 qp_log = []          # every solvers.qp call: dict(P,q,G,h,A,b,result)
 qp_log_enabled = False
+diverge_factor = None  # None = cvxopt behaviour; a number = the kernels' documented early exit (oracle/coneqp.py)
 
 
 def install():
@@ -81,7 +82,7 @@ def install():
 
     def qp(P, q, G=None, h=None, A=None, b=None, **kw):
         arr = lambda m: None if m is None else np.asarray(m.a if isinstance(m, _Matrix) else m, dtype=np.float64)
-        res = _coneqp.qp(arr(P), arr(q), arr(G), arr(h), arr(A), arr(b))
+        res = _coneqp.qp(arr(P), arr(q), arr(G), arr(h), arr(A), arr(b), diverge_factor=diverge_factor)
         if qp_log_enabled:
             qp_log.append(dict(P=arr(P), q=arr(q), G=arr(G), h=arr(h), A=arr(A), b=arr(b), result=res))
         out = dict(res)

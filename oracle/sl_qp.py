@@ -95,10 +95,11 @@ def qp_matrices(l_min, l_max, start_l, start_dl, start_ddl, dp_sampling_res=2,
     return P, q, G, h, A, b
 
 
-def quadratic_planning(l_min, l_max, start_l, start_dl, start_ddl, **kw):
-    """Quadratic_planning (path_planning.py:78-219).  Returns (l, dl, ddl, info)."""
+def quadratic_planning(l_min, l_max, start_l, start_dl, start_ddl, diverge_factor=None, **kw):
+    """Quadratic_planning (path_planning.py:78-219).  Returns (l, dl, ddl, info).
+    diverge_factor: None = cvxopt's behaviour; a number = the kernels' documented early exit (oracle/coneqp.py)."""
     P, q, G, h, A, b = qp_matrices(l_min, l_max, start_l, start_dl, start_ddl, **kw)
-    res = coneqp.qp(P, q, G, h, A, b)
+    res = coneqp.qp(P, q, G, h, A, b, diverge_factor=diverge_factor)
     x = res["x"]
     return x[0::3].copy(), x[1::3].copy(), x[2::3].copy(), res
 

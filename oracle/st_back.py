@@ -171,11 +171,11 @@ def speed_qp_cone_form(m):
     return m["H"], m["f"].reshape(-1), np.vstack(rows), np.concatenate(rhs), m["Aeq"].T.copy(), m["beq"].reshape(-1)
 
 
-def speed_qp(v0, a0, dp_s, dp_t, s_lb, s_ub, sd_lb, sd_ub, **kw):
+def speed_qp(v0, a0, dp_s, dp_t, s_lb, s_ub, sd_lb, sd_ub, diverge_factor=None, **kw):
     """speed_QP with repairs R1/R2.  Returns (qp_s, qp_s_dot, qp_s_dot2, relative_time) of length 17, NaN padded,
     and the coneqp info dict."""
     m = speed_qp_matrices(v0, a0, dp_s, dp_t, s_lb, s_ub, sd_lb, sd_ub, **kw)
-    info = coneqp.qp(*speed_qp_cone_form(m))
+    info = coneqp.qp(*speed_qp_cone_form(m), diverge_factor=diverge_factor)
     X = info["x"]
     out = [np.ones(N_QP) * np.nan for _ in range(4)]
     for i in range(1, m["qp_size"] + 1):

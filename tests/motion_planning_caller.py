@@ -1,0 +1,154 @@
+"""The caller side of the drop-in boundary: the per-frame planning loop of the reference's driver scripts.
+
+Test helper.  The reference's `motion_planning(conn)` (test_9.py:92-221) is the function that calls the planner
+hot path in production: a forked child that blocks on `conn.recv()`, runs ~12 planner calls and `conn.send()`s the
+Cartesian path back.  Replaying it against the drop-in package is the end-to-end proof of "drops in unchanged".
+
+Two sources of that function are supported:
+  * `reference_function_text()` - the UNMODIFIED source text of test_9.motion_planning, cut out of
+    /root/reference/test_9.py with `ast` (the module itself cannot be imported: it needs a CARLA server).  Only
+    available where the reference tree exists (the build container).
+  * `motion_planning` below - a restatement of the same loop, used on the GPU box where the reference tree does not
+    exist (reference sources are never copied into this repository).  tests/test_motion_planning_replay.py proves on
+    the CPU, where both exist, that the restatement issues the same planner calls with the same keywords in the
+    same order (AST comparison) and produces bit-identical `conn.send` payloads when both run on the reference's
+    own planner modules.
+Both are executed with `planning_utils` / `path_planning` taken from the caller's globals, exactly like the
+reference's `from planner import planning_utils, path_planning` (test_9.py:26).
+"""
+import ast
+import math
+import os
+
+REFERENCE_DRIVER = os.path.join(os.environ.get("EMP_REFERENCE_ROOT", "/root/reference"), "test_9.py")
+
+
+class ReplayDone(Exception):
+    """Raised by FakePipe.recv() when the recorded frames are exhausted (the reference loop is `while 1`)."""
+
+
+class FakePipe:
+    """Stands in for one end of multiprocessing.Pipe(): recv() hands out recorded messages, send() records payloads."""
+
+    def __init__(self, messages, feedback=True):
+        self.messages = list(messages)
+        self.sent = []
+        self.feedback = feedback
+        self._k = 0
+
+    def recv(self):
+        if self._k >= len(self.messages):
+            raise ReplayDone()
+        msg = list(self.messages[self._k])
+        if self.feedback and self.sent:                      # test_9.py:395 - the match index comes back from the planner
+            msg[7] = self.sent[-1][1]
+        self._k += 1
+        return tuple(msg)
+
+    def send(self, payload):
+        self.sent.append(payload)
+
+
+def reference_function_text(path=REFERENCE_DRIVER, name="motion_planning"):
+    """Source text of the reference's own per-frame loop, or None where the reference tree is absent."""
+    if not os.path.exists(path):
+        return None
+    src = open(path, encoding="utf-8").read()
+    for node in ast.parse(src).body:
+        if isinstance(node, ast.FunctionDef) and node.name == name:
+            return ast.get_source_segment(src, node)
+    raise LookupError("%s not found in %s" % (name, path))
+
+
+def compile_caller(text, planning_utils, path_planning):
+    """exec() a motion_planning source text with the given planner modules as its globals."""
+    import time
+    import numpy as np
+    ns = {"planning_utils": planning_utils, "path_planning": path_planning, "time": time, "math": math, "np": np}
+    exec(compile(text, "<motion_planning>", "exec"), ns)
+    return ns["motion_planning"]
+
+
+def planner_call_sequence(text):
+    """[(module.function, number of positional arguments, sorted keyword names), ...] in source order."""
+    calls = []
+    for node in ast.walk(ast.parse(text)):
+        if isinstance(node, ast.Call) and isinstance(node.func, ast.Attribute) and isinstance(node.func.value, ast.Name) \
+                and node.func.value.id in ("planning_utils", "path_planning"):
+            calls.append((node.lineno, node.col_offset, "%s.%s" % (node.func.value.id, node.func.attr), len(node.args),
+                          tuple(sorted(k.arg for k in node.keywords))))
+    return [c[2:] for c in sorted(calls)]
+
+
+# ---- the restatement -----------------------------------------------------------------------------------------
+# `planning_utils` and `path_planning` are injected by compile_caller / by the importer's globals.
+
+def motion_planning(conn):
+    ego_length, obstacle_length = 2.910, 3
+    while 1:
+        static_obs, dynamic_obs, ego_xy, start_xy, ego_v, ego_a, route, match = conn.recv()
+        match, _ = planning_utils.find_match_points(xy_list=[start_xy], frenet_path_node_list=route,    # noqa: F821
+                                                    is_first_run=False, pre_match_index=match[0])
+        window = planning_utils.sampling(match[0], route, back_length=10, forward_length=50)            # noqa: F821
+        line = planning_utils.smooth_reference_line(window)                                             # noqa: F821
+        s_map = planning_utils.cal_s_map_fun(line, origin_xy=ego_xy)                                    # noqa: F821
+        obs_s, obs_l = [], []
+        if len(static_obs) != 0 and static_obs[0][-1] <= 30:
+            obs_s, obs_l = planning_utils.cal_s_l_fun([(o[0], o[1]) for o in static_obs], line, s_map)  # noqa: F821
+        start_s, start_l = planning_utils.cal_s_l_fun([start_xy], line, s_map)                          # noqa: F821
+        if len(dynamic_obs) != 0:
+            gap, v_obs = dynamic_obs[0][2], dynamic_obs[0][3]
+            closing = math.sqrt(ego_v[0] ** 2 + ego_v[1] ** 2) - v_obs
+            t_meet = (gap - ego_length / 2 - obstacle_length / 2) / closing
+            t_leave = t_meet + (ego_length + obstacle_length) / closing
+            s_meet = start_s[0] + gap + v_obs * t_meet - obstacle_length / 2
+            s_leave = start_s[0] + gap + v_obs * t_leave + obstacle_length / 2
+            s_mid = s_meet + (s_leave - s_meet) / 2
+            if s_leave < 80:                                  # three virtual static obstacles on the reference line
+                obs_s.extend([s_meet - 10, s_mid, s_leave])
+                obs_l.extend([0, 0, 0])
+        l0, _, _, _, dl0, _, ddl0 = planning_utils.cal_s_l_deri_fun(xy_list=[start_xy], V_xy_list=[ego_v],  # noqa: F821
+                                                                    a_xy_list=[ego_a], local_path_xy_opt=line,
+                                                                    origin_xy=start_xy)
+        dp_s, dp_l = path_planning.DP_algorithm(obs_s, obs_l, plan_start_s=start_s[0], plan_start_l=l0[0],  # noqa: F821
+                                                plan_start_dl=dl0[0], plan_start_ddl=ddl0[0])
+        dp_s, dp_l = dp_s[::2], dp_l[::2]
+        l_min, l_max = path_planning.cal_lmin_lmax(dp_path_s=dp_s, dp_path_l=dp_l, obs_s_list=obs_s,    # noqa: F821
+                                                   obs_l_list=obs_l, obs_length=5, obs_width=5)
+        qp_l, _, _ = path_planning.Quadratic_planning(l_min, l_max, plan_start_l=l0[0],                 # noqa: F821
+                                                      plan_start_dl=dl0[0], plan_start_ddl=ddl0[0])
+        path_s = [dp_s[0]] + [(dp_s[i] + dp_s[i - 1]) / 2 for i in range(1, len(qp_l))] + [dp_s[-1]]
+        path_l = [qp_l[0]] + [(qp_l[i] + qp_l[i - 1]) / 2 for i in range(1, len(qp_l))] + [qp_l[-1]]
+        cart = path_planning.frenet_2_x_y_theta_kappa(plan_start_s=start_s[0], plan_start_l=start_l[0],  # noqa: F821
+                                                      enriched_s_list=path_s, enriched_l_list=path_l,
+                                                      frenet_path_opt=line, s_map=s_map)
+        conn.send((cart, match, path_s, path_l))
+
+
+def restated_function_text():
+    import inspect
+    return inspect.getsource(motion_planning)
+
+
+def replay(text, planning_utils, path_planning, messages, feedback=True):
+    """Run a motion_planning text on recorded messages; returns the list of conn.send payloads."""
+    fn = compile_caller(text, planning_utils, path_planning)
+    pipe = FakePipe(messages, feedback=feedback)
+    try:
+        fn(pipe)
+    except ReplayDone:
+        pass
+    return pipe.sent
+
+
+def messages_from_golden(g):
+    """Rebuild the recorded `conn.recv()` tuples from tests/golden/motion_planning.npz."""
+    route = [tuple(float(v) for v in row) for row in g["route"]]
+    msgs = []
+    for f in range(len(g["ego"])):
+        stat = [tuple(float(v) for v in g["static"][f, j]) for j in range(int(g["n_static"][f]))]
+        dyn = [tuple(float(v) for v in g["dynamic"][f, j]) for j in range(int(g["n_dynamic"][f]))]
+        pt = lambda a: (float(a[f, 0]), float(a[f, 1]))
+        msgs.append((stat, dyn, pt(g["ego"]), pt(g["pred"]), pt(g["vel"]), pt(g["acc"]), route,
+                     [int(v) for v in g["first_match"]]))
+    return msgs

@@ -22,7 +22,7 @@ def Gt_mul(v, d1, d2):
 
 
 def solve_qp(lmin, lmax, st, ds=2.0, w_l=1000, w_ddl=3000, w_dddl=150, w_c=250, w_el=40, w_edl=40, w_eddl=40,
-             d1=3, d2=3, host_w=3, maxiters=100, abstol=1e-7, reltol=1e-6, feastol=1e-7, trace=None):
+             d1=3, d2=3, host_w=3, maxiters=100, abstol=1e-7, reltol=1e-6, feastol=1e-7, trace=None, diverge_factor=None):
     """Returns (x [n,3], status, iterations)."""
     lmin = np.asarray(lmin, dtype=np.float64)
     lmax = np.asarray(lmax, dtype=np.float64)
@@ -153,6 +153,7 @@ def solve_qp(lmin, lmax, st, ds=2.0, w_l=1000, w_ddl=3000, w_dddl=150, w_c=250, 
     if tz >= -1e-8 * max(nrms, 1.0):
         z = z + (1.0 + tz)
     gap = (s * z).sum()
+    gap_min = gap
     resx0 = max(1.0, np.sqrt((q * q).sum()))
     resy0 = 1.0
     resz0 = max(1.0, np.sqrt((h * h).sum()))
@@ -178,6 +179,9 @@ def solve_qp(lmin, lmax, st, ds=2.0, w_l=1000, w_ddl=3000, w_dddl=150, w_c=250, 
             return x, 'unknown', it
         if not np.isfinite(gap + resx + resz):
             return x, 'unknown', it
+        if diverge_factor and it > 0 and gap > diverge_factor * gap_min:
+            return x, 'unknown', it
+        gap_min = min(gap_min, gap)
         isv = 1.0 / s
         w = z * isv
         F = factor(w)

@@ -3,10 +3,11 @@
 Checker = oracle/ (closed-form mode) and tests/golden (outputs of the unmodified reference).
 Tolerances (stated per test):
   DP   : lattice row indices identical; densified length identical; |dl| <= 1e-12 vs the oracle
-         (bit-for-bit expected: same association order, no FMA); <= 1e-9 m vs the reference on
-         lattice A, <= 1e-4 m on lattices B/C (reference noise of its 6x6 inverse).
-  QP   : per-frame RMS(l_gpu - l_oracle) <= 1e-4 m (north_star) on frames both call optimal;
-         observed ~1e-10.  Iteration counts are compared and reported.
+         (bit-for-bit expected: same association order, no FMA); vs the unmodified reference (512 / 128 / 1024
+         golden frames of lattices A / B / C): <= 1e-10 m on A, <= 1e-9 m on B/C (observed 2.9e-12 /
+         2.8e-11 / 3.8e-11, the reference's own 6x6-inverse noise), zero row or length flips.
+  QP   : per-frame RMS(l_gpu - l_oracle) <= 1e-4 m (north_star) on EVERY frame, optimal or not; status agreement
+         100 %; iteration counts equal on >= 99 %.  Observed numbers are written to gpurun_out/parity/.
 """
 import numpy as np
 import pytest
@@ -29,7 +30,7 @@ def _scenes_from(g):
     return api.pack_scenes(g["obs_s"], g["obs_l"], g["nobs"], g["s0"], g["l0"], g["dl0"], g["ddl0"])
 
 
-@pytest.mark.parametrize("tag,tol_ref", [("A", 1e-9), ("B", 1e-4), ("C", 1e-4)])
+@pytest.mark.parametrize("tag,tol_ref", [("A", 1e-10), ("B", 1e-9), ("C", 1e-9)])
 def test_dp_matches_reference_golden(planner, tag, tol_ref):
     from emplanner_carla_b200 import api
     g = load_golden("sl_%s.npz" % tag)
@@ -46,6 +47,8 @@ def test_dp_matches_reference_golden(planner, tag, tol_ref):
         assert np.array_equal(view.enr_s[b, :n[b]], g["ref_s"][b, :n[b]])
         worst = max(worst, np.abs(view.enr_l[b, :n[b]] - g["ref_l"][b, :n[b]]).max())
     print("lattice", tag, "max |l_gpu - l_reference| = %.3e" % worst)
+    _record("sl_dp_%s" % tag, dict(lattice=tag, frames=int(len(n)), row_flips=0, length_flips=0, worst_abs_dl_vs_reference=worst,
+                                   tolerance=tol_ref))
     assert worst <= tol_ref
 
 
@@ -72,35 +75,74 @@ def test_dp_bit_exact_vs_oracle(planner, name):
         assert np.abs(view.enr_l[b, :nb] - el).max() <= 1e-12
 
 
+def _qp_compare(view, g, key, ok, api):
+    """Per-frame comparison of the QP part of plan records with golden arrays `<key>_l/_iters/_optimal`."""
+    st = view.qp_status.astype(int)
+    opt_gpu = st == api.QP_OK
+    opt_ref = g[key + "_optimal"] == 1
+    r = dict(frames=int(ok.sum()), optimal=int((opt_ref & ok).sum()), status_disagree=int((opt_gpu != opt_ref)[ok].sum()),
+             iter_mismatch_optimal=0, iter_mismatch_unknown=0, worst_rms_optimal=0.0, worst_rms_unknown=0.0,
+             worst_abs_optimal=0.0)
+    for b in np.where(ok)[0]:
+        n = int(view.n_qp[b])
+        assert n == (g["ref_n"][b] + 1) // 2
+        d = view.qp_l[b, :n] - g[key + "_l"][b, :n]
+        rms = float(np.sqrt(np.mean(d * d)))
+        kind = "optimal" if opt_ref[b] else "unknown"
+        r["worst_rms_" + kind] = max(r["worst_rms_" + kind], rms)
+        r["iter_mismatch_" + kind] += int(view.qp_iters[b] != g[key + "_iters"][b])
+        if opt_ref[b]:
+            r["worst_abs_optimal"] = max(r["worst_abs_optimal"], float(np.abs(d).max()))
+    return r
+
+
+def _record(name, obj):
+    """Observed parity numbers go to gpurun_out/parity/ (collected into profiles/parity_r2.json by tools/parity_report.py)."""
+    import json
+    import os
+    from conftest import ROOT
+    d = os.path.join(ROOT, "gpurun_out", "parity")
+    try:
+        os.makedirs(d, exist_ok=True)
+        with open(os.path.join(d, name + ".json"), "w") as f:
+            json.dump(obj, f, indent=1, sort_keys=True)
+    except OSError:
+        pass
+
+
 @pytest.mark.parametrize("tag", ["A", "B", "C"])
-def test_plan_matches_golden_qp(planner, tag):
-    """Full DP -> [::2] -> corridor -> QP against the golden corridor and QP solution."""
+def test_plan_matches_golden_qp_on_every_frame(planner, tag):
+    """Full DP -> [::2] -> corridor -> QP against the golden corridor and QP solution, EVERY frame (optimal or not).
+
+    (1) kernel defaults (divergence exit, EmpQpParams.diverge_factor = 2) against the oracle run with the same rule
+        (`qpd_*`): status must agree on 100 % of the frames, RMS(l) <= 1e-4 m (north_star) on optimal AND unknown frames.
+    (2) cvxopt's rule (diverge_factor = 0: iterate until the factorisation breaks down) against `qp_*`: status must agree
+        on 100 % of the frames and optimal frames must match to 1e-4 m; the iterate of an 'unknown' frame is not a
+        numerically reproducible quantity under this rule (see include/emplanner.h) - its distance is recorded only."""
     from emplanner_carla_b200 import api
     g = load_golden("sl_%s.npz" % tag)
     lat = lattice_from_golden(g)
-    dp, qp = api.dp_params(**lat.kwargs()), api.qp_params()
-    view, _ = planner.plan(_scenes_from(g), dp, qp)
-    B = len(g["s0"])
-    st = view.qp_status.astype(int)
-    assert np.array_equal(st == api.QP_CORRIDOR_INDEX, g["cor_index_error"] == 1)
-    opt_ref = g["qp_optimal"] == 1
-    opt_gpu = st == api.QP_OK
-    agree = opt_ref == opt_gpu
-    print("lattice", tag, "status agreement %d/%d" % (agree.sum(), B))
-    assert agree.mean() >= 0.97
-    worst, it_mismatch, cnt = 0.0, 0, 0
-    for b in range(B):
-        if not (opt_ref[b] and opt_gpu[b]):
-            continue
-        n = int(view.n_qp[b])
-        assert n == (g["ref_n"][b] + 1) // 2
-        rms = np.sqrt(np.mean((view.qp_l[b, :n] - g["qp_l"][b, :n]) ** 2))
-        worst = max(worst, rms)
-        it_mismatch += int(view.qp_iters[b] != g["qp_iters"][b])
-        cnt += 1
-    print("lattice", tag, "frames", cnt, "worst RMS l error %.3e" % worst, "iteration mismatches", it_mismatch)
-    assert worst <= 1e-4
-    assert it_mismatch <= max(1, cnt // 20)
+    dp = api.dp_params(**lat.kwargs())
+    rec = _scenes_from(g)
+    ok = g["cor_index_error"] == 0
+    view, _ = planner.plan(rec, dp, api.qp_params())
+    assert np.array_equal(view.qp_status.astype(int) == api.QP_CORRIDOR_INDEX, ~ok)
+    r1 = _qp_compare(view, g, "qpd", ok, api)
+    unknown = ok & (g["qpd_optimal"] == 0)
+    assert np.all(view.qp_status[unknown] == api.QP_UNKNOWN_DIVERGED)
+    view0, _ = planner.plan(rec, dp, api.qp_params(diverge_factor=0))
+    r2 = _qp_compare(view0, g, "qp", ok, api)
+    print("lattice", tag, "divergence exit:", r1)
+    print("lattice", tag, "cvxopt rule    :", r2)
+    _record("sl_qp_%s" % tag, dict(lattice=tag, divergence_exit=r1, cvxopt_rule=r2))
+    assert r1["status_disagree"] == 0 and r2["status_disagree"] == 0
+    assert r1["worst_rms_optimal"] <= 1e-4 and r1["worst_rms_unknown"] <= 1e-4
+    assert r2["worst_rms_optimal"] <= 1e-4
+    assert r1["iter_mismatch_optimal"] + r1["iter_mismatch_unknown"] <= max(1, r1["frames"] // 100)
+    assert r2["iter_mismatch_optimal"] <= max(1, r2["frames"] // 100)
+    # frames that converge are untouched by the divergence exit: same bits out of the kernel either way
+    opt = ok & (g["qp_optimal"] == 1)
+    assert np.array_equal(view.qp_l[opt], view0.qp_l[opt]) and np.array_equal(view.qp_iters[opt], view0.qp_iters[opt])
 
 
 def test_qp_direct_and_corridor_entry_points(planner):

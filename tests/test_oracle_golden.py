@@ -25,11 +25,15 @@ def test_dp_inv_mode_is_bit_exact_to_reference(tag, frames):
         assert np.array_equal(rows, g["rows"][b]) or g["nobs"][b] == 0
 
 
-@pytest.mark.parametrize("tag,tol", [("A", 1e-9), ("B", 1e-4), ("C", 1e-4)])
-def test_dp_closed_form_matches_reference(tag, tol):
-    """mode='closed' (what the CUDA kernel implements): same rows and length on every golden frame,
-    l within the reference's own inversion noise."""
+@pytest.mark.parametrize("tag,tol,frames", [("A", 1e-10, 512), ("B", 1e-9, 128), ("C", 1e-9, 256)])
+def test_dp_closed_form_matches_reference(tag, tol, frames):
+    """mode='closed' (what the CUDA kernel implements) against the unmodified reference: same rows and length, l within
+    SURVEY 8(c)'s 1e-9 m (1e-10 on lattice A).  The golden generator evaluated this on EVERY golden frame (512 / 128 /
+    1024) and stored the result (`closed_*`); the first `frames` frames are recomputed here with the batched oracle."""
     g = load_golden("sl_%s.npz" % tag)
+    assert np.all(g["closed_rows_equal"] == 1) and np.all(g["closed_n_equal"] == 1), "row / length flip vs the reference"
+    assert np.nanmax(g["closed_dl"]) <= tol, np.nanmax(g["closed_dl"])
+    g = {k: (g[k][:frames] if g[k].ndim and len(g[k]) == len(g["s0"]) else g[k]) for k in g.files}
     lat = lattice_from_golden(g)
     rows, ns, nl, _ = sl_dp.dp_batch(g["obs_s"], g["obs_l"], g["nobs"], g["s0"], g["l0"], g["dl0"], g["ddl0"],
                                      **lat.kwargs())
@@ -78,7 +82,7 @@ def test_quirk_ledger_dp():
 def test_corridor_and_qp_against_golden(tag):
     g = load_golden("sl_%s.npz" % tag)
     checked = 0
-    for b in range(0, len(g["s0"]), 3):
+    for b in range(0, len(g["s0"]), max(3, len(g["s0"]) // 40)):
         n = g["ref_n"][b]
         K = int(g["nobs"][b])
         s, l = g["ref_s"][b, :n:2], g["ref_l"][b, :n:2]
@@ -93,6 +97,15 @@ def test_corridor_and_qp_against_golden(tag):
         assert (info["status"] == "optimal") == bool(g["qp_optimal"][b])
         assert info["iterations"] == g["qp_iters"][b]
         assert np.array_equal(ql, g["qp_l"][b, :m])
+        # the same solve with the kernels' documented divergence exit (golden qpd_*): identical on converging frames
+        dl_, _, _, info_d = sl_qp.quadratic_planning(lmin, lmax, g["l0"][b], g["dl0"][b], g["ddl0"][b],
+                                                      diverge_factor=float(g["diverge_factor"]))
+        assert (info_d["status"] == "optimal") == bool(g["qpd_optimal"][b]) == bool(g["qp_optimal"][b])
+        assert info_d["iterations"] == g["qpd_iters"][b] and np.array_equal(dl_, g["qpd_l"][b, :m])
+        if info["status"] == "optimal":
+            assert np.array_equal(dl_, ql)
+        else:
+            assert info_d["iterations"] <= info["iterations"]
         checked += 1
     assert checked > 3
 
