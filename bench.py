@@ -3,25 +3,36 @@
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--batch B] [--lattice C]
 
-One "step" = one pass of the hot path (DP kernel -> corridor+QP kernel [-> gather of the plan records when
-N > 1]) over one batch of synthetic Frenet scenes.  Default workload = BASELINE.json configs[1]:
-batch 4096 per GPU, 60x11 S-L lattice, 0-8 random obstacles (weak scaling: per-GPU batch fixed).
+One "step" = one pass of the hot path (schedule -> DP kernel -> corridor+QP kernel [-> gather of the plan records when
+N > 1]) over one batch of synthetic Frenet scenes.  Default workload = BASELINE.json configs[1]: batch 4096 per GPU,
+60x11 S-L lattice, 0-8 random obstacles (weak scaling: per-GPU batch fixed).
 
-  value     frames/s over exactly K steps, inputs resident in HBM, one start and one end CUDA event on the
-            launching stream, max over ranks; --pipeline P (default 2) batches are in flight: step k runs on
-            stream k % P with its own plan/gather buffer, so step k+1's DP kernel overlaps step k's QP kernel
-  pipeline  the same K steps strictly one after the other (value_serial_steps); kernels_ms and roofline come
-            from this serial pass (events around each kernel)
-  e2e       frames/s through the host-buffer C ABI (emp_sl_plan_submit / emp_sl_plan_wait, P slots; emp_sl_plan_host
-            for P = 1): page-locked host buffers in and out, H2D + D2H of every step inside the timed region
+  value     frames/s over exactly K steps, inputs resident in HBM, one start and one end CUDA event on the launching
+            stream, barrier + synchronize on both sides, max over ranks.  --pipeline P (default 2) batches are in flight
+            (step k on stream k % P).  The K-step region is repeated until --min-seconds of timed work has
+            accumulated; `value` / `ms_per_step` are those of the MEDIAN region (min / max in `regions`).
+            L2: steps rotate over enough scene / plan buffer sets to exceed twice the L2 capacity, so every step reads
+            and writes memory that has been evicted since its last use - no flush kernel inside the timed region.
+  pipeline  the same K steps strictly one after the other; kernels_ms and roofline come from this serial pass
+            (CUDA events around each kernel)
+  e2e       N = 1: frames/s through the host-buffer C ABI (emp_sl_plan_submit / emp_sl_plan_wait, P slots): page-locked
+            host buffers in and out, H2D + D2H of every step inside the timed region (wall clock).
+            N > 1: the same through the multi-GPU product path: every rank copies its shard's scenes from page-locked
+            host memory, plans, gathers (so every GPU holds the whole batch) and copies its own shard of the plan
+            records back to its host
   roofline  dominant kernel's algorithmic HBM bytes / its CUDA-event duration vs MEASURED_PEAKS hbm_gbs
-  compute   same launch against the FP64 FMA peak measured on this GPU (the binding roofline)
+  compute   the FP64 FMA peak measured on this GPU in this run, next to the ncu FP64-pipe utilisation of the current
+            kernels (profiles/ncu_r2_summary.json, refused when the kernel sources changed since the capture)
   cpu_baseline  the oracle port (numpy float64, oracle/) on a bounded prefix of the same batch, all cores
-`--impl reference` times that CPU port alone (the reference itself is Python that cannot travel to
+  extra     secondary configurations of BASELINE.json measured in the same run: config2 (8192 frames per GPU = 65536
+            on 8 GPUs) and config4 (full EM cycle, 2048 frames per GPU = 16384 on 8 GPUs)
+`--impl reference` times that CPU port alone on the same frames (the reference itself is Python that cannot travel to
 the GPU box; the port is pinned to it bit-for-bit / by golden vectors).
 """
 import argparse
+import hashlib
 import json
+import math
 import os
 import sys
 import threading
@@ -34,18 +45,10 @@ import numpy as np  # noqa: E402
 
 METRIC = "planning frames/sec (S-L DP+QP batch)"
 UNIT = "frames/s"
-# Algorithmic (compulsory) HBM bytes per frame, float64 (DESIGN.md "Kernels").
-SCENE_BYTES = 164
-
-
-# Static ncu facts of the current kernels (one `ncu --set full` capture per change, see profiles/): the FP64 pipe
-# utilisation is the compute-roofline fraction; dram bytes per launch (batch 4096) go into roofline.traffic.
-NCU_STATIC = {
-    "C_60x11": {"fp64_pipe_active": {"sl_dp_kernel": 0.213, "sl_qp_kernel": 0.381},
-                "issue_active": {"sl_dp_kernel": 0.609, "sl_qp_kernel": 0.434},
-                "dram_bytes_per_launch": {"sl_dp_kernel": 919040 + 107520, "sl_qp_kernel": 5506048},
-                "source": "profiles/r1_ncu_sl_final_summary.txt (batch 4096, lattice C, serial pass)"},
-}
+SCENE_BYTES = 164                 # algorithmic (compulsory) input bytes per frame
+DIVERGE_FACTOR = 2.0              # EmpQpParams.diverge_factor default; the CPU port runs the same stopping rule
+NCU_SUMMARY = os.path.join(ROOT, "profiles", "ncu_r2_summary.json")
+KERNEL_SOURCES = ("emplanner_carla_b200/csrc/sl_dp.cu", "emplanner_carla_b200/csrc/sl_qp.cu")
 
 
 def algorithmic_bytes(n_enr, n_qp):
@@ -55,11 +58,32 @@ def algorithmic_bytes(n_enr, n_qp):
 
 
 def dp_flops(lat, nobs_mean):
-    return lat.edges * (390 + 80 * nobs_mean)                    # SURVEY.md §8(d) operation count of the reference
+    return lat.edges * (390 + 80 * nobs_mean)                    # SURVEY.md 8(d) operation count of the reference
 
 
-def qp_flops(n, iters_mean):
-    return 1500.0 * n * iters_mean                               # banded IPM ~1.5 k flops per station per iteration
+def workload_string(batch, lat, world=1):
+    return ("batch=%d/GPU synthetic Frenet scenes, %dx%d S-L lattice (%s), 0-8 random obstacles, "
+            "DP->[::2]->corridor->QP" % (batch, lat.col, lat.row, lat.name))
+
+
+def source_hashes():
+    out = {}
+    for rel in KERNEL_SOURCES:
+        with open(os.path.join(ROOT, rel), "rb") as f:
+            out[os.path.basename(rel)] = hashlib.sha256(f.read()).hexdigest()[:16]
+    return out
+
+
+def ncu_facts():
+    """Per-kernel ncu metrics of the CURRENT kernels, or a note saying why there are none."""
+    try:
+        with open(NCU_SUMMARY) as f:
+            d = json.load(f)
+    except Exception:
+        return None, "no %s" % os.path.relpath(NCU_SUMMARY, ROOT)
+    if d.get("source_sha") != source_hashes():
+        return None, "%s is stale: kernel sources changed since the capture" % os.path.relpath(NCU_SUMMARY, ROOT)
+    return d, os.path.relpath(NCU_SUMMARY, ROOT)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -134,25 +158,28 @@ def _cpu_worker(args):
             lmin, lmax = sl_qp.corridor(es[::2], el[::2], sc["obs_s"][b, :K], sc["obs_l"][b, :K], 5, 5)
         except IndexError:
             continue
-        _, _, _, info = sl_qp.quadratic_planning(lmin, lmax, sc["l0"][b], sc["dl0"][b], sc["ddl0"][b])
+        # same stopping rule as the kernels (the divergence exit), so both arms do the same work on every frame
+        _, _, _, info = sl_qp.quadratic_planning(lmin, lmax, sc["l0"][b], sc["dl0"][b], sc["ddl0"][b],
+                                                 diverge_factor=DIVERGE_FACTOR)
         n_opt += info["status"] == "optimal"
     return hi - lo, t_dp, time.perf_counter() - t0, n_opt
 
 
-def cpu_port_throughput(lat_name, config_id, frames_per_core, cores):
-    """frames/s of the oracle port with `cores` processes, each on its own prefix slice of the batch."""
+def cpu_port_throughput(lat_name, config_id, frames, cores, total):
+    """frames/s of the oracle port with `cores` processes over the first `frames` frames of the `total`-frame batch."""
     import multiprocessing as mp
-    total = frames_per_core * cores
-    jobs = [(lat_name, config_id, c * frames_per_core, (c + 1) * frames_per_core, total) for c in range(cores)]
+    frames = max(cores, min(int(frames), total))
+    bounds = [round(c * frames / cores) for c in range(cores + 1)]
+    jobs = [(lat_name, config_id, bounds[c], bounds[c + 1], total) for c in range(cores) if bounds[c + 1] > bounds[c]]
     t0 = time.perf_counter()
-    if cores == 1:
+    if len(jobs) == 1:
         res = [_cpu_worker(jobs[0])]
     else:
-        with mp.get_context("fork").Pool(cores) as pool:
+        with mp.get_context("fork").Pool(len(jobs)) as pool:
             res = pool.map(_cpu_worker, jobs)
     wall = time.perf_counter() - t0
-    frames = sum(r[0] for r in res)
-    return frames / wall, frames, wall, sum(r[1] for r in res) / max(sum(r[2] for r in res), 1e-9)
+    done = sum(r[0] for r in res)
+    return done / wall, done, wall, sum(r[1] for r in res) / max(sum(r[2] for r in res), 1e-9)
 
 
 def host_cores():
@@ -163,33 +190,334 @@ def host_cores():
 
 
 # ------------------------------------------------------------------------------------------------
-def run_reference(args, lat_name, config_id):
-    """--impl reference: the CPU port of the reference path, all host cores, bounded sample per step."""
+def run_reference(args, lat, config_id):
+    """--impl reference: the CPU port of the reference path, all host cores, on the product arm's own frames."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     cores = host_cores()
-    per_core = max(2, args.cpu_frames // cores)
+    total = args.batch
+    # bounded sample: the whole batch per step when the run fits ~200 s, otherwise a prefix of it
+    rate, _, _, _ = cpu_port_throughput(args.lattice, config_id, 2 * cores, cores, total)          # untimed probe
+    budget = 200.0 / max(args.steps + min(args.warmup, 1), 1)
+    frames = total if args.cpu_frames <= 0 else min(total, args.cpu_frames)
+    frames = int(max(cores, min(frames, rate * budget)))
     for _ in range(min(args.warmup, 1)):
-        cpu_port_throughput(lat_name, config_id, 2, cores)
+        cpu_port_throughput(args.lattice, config_id, min(frames, 4 * cores), cores, total)
     t0 = time.perf_counter()
-    frames = 0
+    done = 0
     for _ in range(args.steps):
-        _, f, _, _ = cpu_port_throughput(lat_name, config_id, per_core, cores)
-        frames += f
+        _, f, _, _ = cpu_port_throughput(args.lattice, config_id, frames, cores, total)
+        done += f
     wall = time.perf_counter() - t0
-    val = frames / wall
-    sample = "%d frames/step (prefix of the batch-%d workload, %d per core), numpy float64 port of DP->corridor->QP" % (
-        per_core * cores, args.batch, per_core)
+    val = done / wall
+    if frames == total:
+        sample = "all %d frames of the batch per step" % total
+    else:
+        sample = "the first %d frames of the batch-%d workload per step (bounded to keep the run within minutes)" % (frames, total)
+    sample += ", numpy float64 port of DP->corridor->QP (oracle/), %d processes" % cores
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * wall / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "batch=%d synthetic Frenet scenes, lattice %s, 0-8 obstacles" % (args.batch, lat_name),
-                       "lattice": lat_name, "batch_per_gpu": args.batch},
+            "config": {"workload": workload_string(args.batch, lat), "lattice": lat.name, "batch_per_gpu": args.batch,
+                       "frames_per_step_timed": frames},
             "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+class SlWorkload:
+    """Device buffers + the step of the S-L planning workload for one per-GPU batch size."""
+
+    def __init__(self, torch, dist, api, sharding, lat, config_id, B, rank, world, dev, gather, P, flush):
+        self.torch, self.dist, self.api, self.world, self.rank, self.dev, self.P = torch, dist, api, world, rank, dev, P
+        self.B, self.lat = B, lat
+        self.dp, self.qp = api.dp_params(**lat.kwargs()), api.qp_params()
+        self.NE = api.max_enriched(self.dp)
+        self.stride = api.plan_stride(self.NE)
+        from emplanner_carla_b200 import scenes
+        sc = scenes.sl_scenes(B * world, lat, config_id)               # each rank plans its own contiguous shard
+        self.shard = {k: v[rank * B:(rank + 1) * B] for k, v in sc.items()}
+        self.rec_host = api.pack_scenes(**self.shard)
+        self.p2p = world > 1 and gather == "p2p"
+        self.gather = gather
+        set_bytes = world * B * self.stride * 8 + self.rec_host.nbytes
+        l2 = int(torch.cuda.get_device_properties(dev).L2_cache_size)
+        if flush:
+            nb = P
+        else:
+            nb = max(P, int(math.ceil(2.0 * l2 / set_bytes)))
+            nb = (nb + P - 1) // P * P                                 # buffer set b is always used on stream b % P
+        self.NB, self.l2_bytes, self.set_bytes = nb, l2, set_bytes
+        self.scenes = [torch.from_numpy(self.rec_host).to(dev) for _ in range(nb)]
+        self.orders = [torch.empty(B, dtype=torch.int32, device=dev) for _ in range(nb)]
+        mk = (lambda: sharding.PeerGatherBuffer(B, self.stride, dev)) if self.p2p else \
+             (lambda: sharding.GatherBuffer(B, self.stride, dev))
+        self.gbufs = [mk() for _ in range(nb)]
+        self.flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev) if flush else None
+        self.main = torch.cuda.current_stream()
+        self.streams = [torch.cuda.Stream(device=dev) for _ in range(P)] if P > 1 else [self.main]
+        self.launches_per_step = 3 + (1 if self.p2p else 0) + (1 if self.p2p else 0)   # order, DP, QP (+ credit wait, consume)
+
+    def step(self, k, ev=None):
+        """Enqueue step k on torch's current stream (buffer set k % NB)."""
+        api, b = self.api, k % self.NB
+        sc, od, gb = self.scenes[b], self.orders[b], self.gbufs[b]
+        st = self.torch.cuda.current_stream()
+        if self.flush is not None:
+            self.flush.fill_(k & 0xFF)
+        if ev:
+            ev[0].record(st)
+        api.order_device(sc, od)
+        if ev:
+            ev[1].record(st)
+        api.dp_device(sc, self.dp, self.NE, plans=gb.mine, order=od)
+        if ev:
+            ev[2].record(st)
+        if self.p2p:
+            gb.plan_qp(sc, self.qp, self.NE, order=od)                 # QP + NVLink peer stores + arrival flag
+        else:
+            api.qp_device(sc, self.qp, self.NE, gb.mine, order=od)
+        if ev:
+            ev[3].record(st)
+        if self.world > 1:
+            if self.p2p:
+                gb.consume()                                           # wait for every shard, hand the buffer back
+            else:
+                gb.all_gather()                                        # one in-place NCCL all-gather of plan records
+        if ev:
+            ev[4].record(st)
+
+    def sync(self):
+        self.torch.cuda.synchronize()
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def region(self, K, k0=0):
+        """Exactly K steps, P in flight; returns the region's duration in ms on this rank (CUDA events)."""
+        torch = self.torch
+        self.sync()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(self.main)
+        if self.P > 1:
+            for s in self.streams:
+                s.wait_event(e0)
+        for k in range(K):
+            with torch.cuda.stream(self.streams[(k0 + k) % self.P]):
+                self.step(k0 + k)
+        if self.P > 1:
+            for s in self.streams:
+                self.main.wait_stream(s)
+        e1.record(self.main)
+        self.sync()
+        return e0.elapsed_time(e1)
+
+    def max_over_ranks(self, values):
+        t = self.torch.tensor(values, dtype=self.torch.float64, device=self.dev)
+        if self.world > 1:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return [float(v) for v in t.tolist()]
+
+    def timed(self, K, warmup, min_seconds, max_regions=400):
+        """Warm up, then repeat the K-step region until min_seconds of timed work; per-region max over ranks."""
+        self.region(max(warmup, 1), 0)                                 # >= `warmup` untimed steps
+        k0 = max(warmup, 1)
+        t_cal = self.max_over_ranks([self.region(K, k0)])[0]           # untimed calibration region
+        k0 += K
+        n = int(min(max_regions, max(3, math.ceil(min_seconds * 1e3 / max(t_cal, 1e-3)))))
+        times = []
+        for _ in range(n):
+            times.append(self.region(K, k0))
+            k0 += K
+        times = self.max_over_ranks(times)
+        return times
+
+    def serial(self, K):
+        """K steps strictly one after the other on the main stream with events around every kernel."""
+        torch = self.torch
+        self.sync()
+        evs = [[torch.cuda.Event(enable_timing=True) for _ in range(5)] for _ in range(K)]
+        for k in range(K):
+            self.step(k, evs[k])
+        self.sync()
+        seg = [sum(e[i].elapsed_time(e[i + 1]) for e in evs) for i in range(4)]
+        seg.append(sum(e[0].elapsed_time(e[4]) for e in evs))
+        return self.max_over_ranks(seg)                                # order, dp, qp, collective, total (ms over K steps)
+
+    def verify_gather(self):
+        """Every buffer set's gathered batch against one NCCL all-gather of the same plan records, bit for bit."""
+        if self.world == 1:
+            return None
+        torch, dist = self.torch, self.dist
+        ok = True
+        tmp = torch.empty((self.world, self.B, self.stride), dtype=torch.float64, device=self.dev)
+        for gb in self.gbufs:
+            dist.all_gather_into_tensor(tmp.view(-1), gb.mine.reshape(-1).clone())
+            torch.cuda.synchronize()
+            ok = ok and bool(torch.equal(tmp.view(torch.int64), gb.full.view(torch.int64)))
+            if self.p2p:
+                ok = ok and int(gb.err.item()) == 0
+        flag = torch.tensor([1 if ok else 0], device=self.dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        return bool(flag.item() == 1)
+
+    def close(self):
+        for gb in self.gbufs:
+            if hasattr(gb, "close"):
+                gb.close()
+
+
+def e2e_single(api, wl, K, warmup, min_seconds, local):
+    """N = 1: host buffers through the C ABI (emp_sl_plan_submit / emp_sl_plan_wait), wall clock."""
+    B, P = wl.B, wl.P
+    planner = api.HostPlanner(max_batch=B, kmax=8, n_enr_max=wl.NE, max_col=wl.lat.col, device=local)
+    outs = [api.pinned_empty((B, wl.stride)) for _ in range(P)]       # page-locked host buffers, like a real ingest path
+    recs = [api.pinned_empty(wl.rec_host.shape) for _ in range(P)]
+    for r in recs:
+        r[:] = wl.rec_host
+
+    def steps(n):
+        if P == 1:
+            for _ in range(n):
+                planner.plan(recs[0], wl.dp, wl.qp, out=outs[0])
+            return
+        for k in range(n):                                             # every step: H2D of its scenes, D2H of its plans
+            if k >= P:
+                planner.plan_wait(k % P)
+            planner.plan_submit(k % P, recs[k % P], wl.dp, wl.qp, outs[k % P])
+        for k in range(min(P, n)):
+            planner.plan_wait(k)
+
+    steps(max(warmup, 3))
+    times, total = [], 0.0
+    while len(times) < 3 or (total < min_seconds and len(times) < 400):
+        t0 = time.perf_counter()
+        steps(K)
+        times.append(time.perf_counter() - t0)
+        total += times[-1]
+    planner.close()
+    api_name = ("emp_sl_plan_submit/emp_sl_plan_wait via HostPlanner.plan_submit, %d slots, " % P if P > 1 else
+                "emp_sl_plan_host via HostPlanner.plan, ") + "page-locked host buffers"
+    return times, int(recs[0].nbytes), int(outs[0].nbytes), api_name
+
+
+def e2e_multi(torch, wl, K, warmup, min_seconds):
+    """N > 1: pinned host scenes -> H2D -> schedule/DP/QP with the fused gather -> consume -> D2H of the rank's own
+    shard of plan records, every step, on the P slot streams; wall clock between barriers, max over ranks."""
+    B, P = wl.B, wl.P
+    pin_in = [torch.from_numpy(wl.rec_host).clone().pin_memory() for _ in range(P)]
+    pin_out = [torch.empty((B, wl.stride), dtype=torch.float64).pin_memory() for _ in range(P)]
+    state = {"k": 10 * wl.NB}                                          # keep buffer set / stream pairing (k % NB, k % P)
+
+    def steps(n):
+        for _ in range(n):
+            k = state["k"]
+            state["k"] += 1
+            b, s = k % wl.NB, k % P
+            with torch.cuda.stream(wl.streams[s]):
+                wl.scenes[b].copy_(pin_in[s], non_blocking=True)
+                wl.step(k)
+                pin_out[s].copy_(wl.gbufs[b].mine, non_blocking=True)
+        torch.cuda.synchronize()
+
+    steps(max(warmup, 3))
+    times, total, n_regions = [], 0.0, None
+    wl.sync()
+    t0 = time.perf_counter()
+    steps(K)
+    cal = wl.max_over_ranks([time.perf_counter() - t0])[0]
+    n_regions = int(min(400, max(3, math.ceil(min_seconds / max(cal, 1e-6)))))
+    for _ in range(n_regions):
+        wl.sync()
+        t0 = time.perf_counter()
+        steps(K)
+        times.append(time.perf_counter() - t0)
+    times = wl.max_over_ranks(times)
+    return times, int(pin_in[0].nbytes) * wl.world, int(pin_out[0].nbytes) * wl.world, (
+        "torch pinned host tensors -> api.order_device / dp_device / sharding.PeerGatherBuffer.plan_qp + consume "
+        "(or qp_device + NCCL all-gather) -> D2H of the rank's own shard; every GPU ends each step holding the gathered "
+        "batch, each rank returns its shard to its host; bytes are summed over ranks")
+
+
+def extra_config2(torch, dist, api, sharding, lat, rank, world, dev, gather, P, K, min_seconds):
+    """BASELINE.json configs[2]: 8192 frames per GPU (65536 on 8 GPUs), same lattice, same step."""
+    wl = SlWorkload(torch, dist, api, sharding, lat, 3, 8192, rank, world, dev, gather, P, False)
+    try:
+        times = wl.timed(K, 3, min_seconds)
+        ok = wl.verify_gather()
+    finally:
+        wl.close()
+    med = float(np.median(times))
+    return {"config": "BASELINE.json configs[2]: %d frames per GPU, global batch %d, lattice %s" % (8192, 8192 * world, lat.name),
+            "global_batch": 8192 * world, "value": 8192 * world * K / (med * 1e-3), "unit": UNIT, "ms_per_step": med / K,
+            "regions": len(times), "gather_verified": ok}
+
+
+def extra_config4(torch, dist, api, lat, rank, world, dev, K, min_seconds):
+    """BASELINE.json configs[4]: full EM cycle (S-L DP -> QP -> path -> S-T DP -> speed QP -> densify -> merge), 2048
+    frames per GPU (16384 on 8 GPUs).  Reported twice: bug-compatible with the reference draft (a full 16-column S-T
+    profile raises IndexError at dp_speed_s[16], speed_planning_test.py:428, so most frames stop before the speed QP)
+    and with the documented repair R3 (EmpSpeedQpParams.repair_full_profile) under which every frame runs the QP."""
+    from emplanner_carla_b200 import scenes
+    B = 2048
+    sc = scenes.cycle_scenes(B * world, lat, 4)
+    sl = {k: v[rank * B:(rank + 1) * B] for k, v in sc["sl"].items()}
+    st = {k: v[rank * B:(rank + 1) * B] for k, v in sc["st"].items()}
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    sl_d = t(api.pack_scenes(**sl))
+    st_d = t(api.pack_st_scenes(st["s_in"], st["s_out"], st["t_in"], st["t_out"], st["v0"]))
+    start = t(np.stack([st["v0"], sc["a0"][rank * B:(rank + 1) * B]], axis=1))
+    now = t(sc["now"][rank * B:(rank + 1) * B])
+    out = {"config": "BASELINE.json configs[4]: full EM cycle, %d frames per GPU, global batch %d, lattice %s, "
+                     "no collective (per-rank outputs)" % (B, B * world, lat.name), "unit": "EM cycles/s"}
+    main = torch.cuda.current_stream()
+    for tag, r3 in (("bug_compatible", False), ("repair_R3", True)):
+        try:
+            sq = api.speed_qp_params(repair_full_profile=r3)
+        except TypeError:
+            if r3:
+                continue
+            sq = api.speed_qp_params()
+        cyc = api.EmCycle(B, api.dp_params(**lat.kwargs()), api.qp_params(), api.st_params(), sq, api.smooth_params())
+
+        def region():
+            torch.cuda.synchronize()
+            if world > 1:
+                dist.barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(main)
+            for _ in range(K):
+                buf = cyc.run(sl_d, st_d, start, now)
+            e1.record(main)
+            torch.cuda.synchronize()
+            if world > 1:
+                dist.barrier()
+            return e0.elapsed_time(e1), buf
+
+        region()
+        times, total = [], 0.0
+        while len(times) < 3 or (total < min_seconds * 1e3 and len(times) < 100):
+            ms, buf = region()
+            times.append(ms)
+            total += ms
+        tt = torch.tensor(times, dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        med = float(np.median(tt.cpu().numpy()))
+        fin = ((buf["merge_status"] == 0) & (buf["dense_status"] == 0) & (buf["qp_status_iters"][:, 0] == 0) &
+               (buf["convex_status"] == 0)).double().mean()
+        ran_qp = (buf["qp_status_iters"][:, 1] > 0).double().mean()
+        stats = torch.stack([fin, ran_qp])
+        if world > 1:
+            dist.all_reduce(stats, op=dist.ReduceOp.SUM)
+            stats = stats / world
+        out[tag] = {"value": B * world * K / (med * 1e-3), "ms_per_cycle_batch": med / K, "regions": len(times),
+                    "frames_finishing_whole_cycle": float(stats[0].item()), "frames_reaching_speed_qp": float(stats[1].item()),
+                    "launches_per_cycle": cyc.N_LAUNCHES}
+    return out
 
 
 # ------------------------------------------------------------------------------------------------
@@ -201,15 +529,19 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=4096, help="frames per GPU per step")
     ap.add_argument("--lattice", default="C", choices=["A", "B", "C"])
-    ap.add_argument("--cpu-frames", type=int, default=1024, help="frames of the CPU baseline sample")
+    ap.add_argument("--cpu-frames", type=int, default=0,
+                    help="frames of the CPU sample (0 = default: 1024 for cpu_baseline, the whole batch for --impl reference)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-flush", action="store_true", help="do not flush L2 between timed steps")
+    ap.add_argument("--flush", action="store_true",
+                    help="flush L2 with a 256 MiB write before every step instead of rotating over buffer sets")
+    ap.add_argument("--min-seconds", type=float, default=0.25, help="timed work to accumulate by repeating the K-step region")
     ap.add_argument("--pipeline", type=int, default=2,
                     help="batches in flight: step k+1's kernels (and copies) overlap step k's on another stream; "
                          "1 = strictly serial steps")
     ap.add_argument("--gather", default="p2p", choices=["p2p", "nccl"],
-                    help="N>1: p2p = plan records stored into peers' buffers by the QP kernel (CUDA IPC, NVLink); "
-                         "nccl = one in-place NCCL all-gather after the kernels")
+                    help="N>1: p2p = plan records stored into peers' buffers by the QP kernel (CUDA IPC, NVLink) with "
+                         "arrival flags; nccl = one in-place NCCL all-gather after the kernels")
+    ap.add_argument("--no-extras", action="store_true", help="skip the config2 / config4 secondary measurements")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
 
@@ -217,11 +549,11 @@ def main():
     lat = scenes.LATTICES[args.lattice]
     config_id = {"A": 0, "B": 1, "C": 2}[args.lattice]
     if args.impl == "reference":
-        return run_reference(args, args.lattice, config_id)
+        return run_reference(args, lat, config_id)
 
     import torch
     import torch.distributed as dist
-    from emplanner_carla_b200 import api
+    from emplanner_carla_b200 import api, sharding
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -233,150 +565,41 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
-    B = args.batch
-    dp, qp = api.dp_params(**lat.kwargs()), api.qp_params()
-    NE = api.max_enriched(dp)
-    stride = api.plan_stride(NE)
-    sc = scenes.sl_scenes(B * world, lat, config_id)                  # each rank plans its own contiguous shard
-    shard = {k: v[rank * B:(rank + 1) * B] for k, v in sc.items()}
-    rec_host = api.pack_scenes(**shard)
-    scenes_d = torch.from_numpy(rec_host).to(dev)
-    from emplanner_carla_b200 import sharding
-    use_p2p = world > 1 and args.gather == "p2p"
+    B, K = args.batch, args.steps
     P = max(1, min(args.pipeline, api.PLAN_SLOTS))
-    gbufs = [sharding.PeerGatherBuffer(B, stride, dev) if use_p2p else sharding.GatherBuffer(B, stride, dev)
-             for _ in range(P)]                                        # one gather buffer per batch in flight
-    gbuf = gbufs[0]
-    mine = gbuf.mine                                                   # kernels write straight into the send slice
-    flush = None if args.no_flush else torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-    stream = torch.cuda.current_stream()
-
-    def step(ev=None, gb=None, st=None):
-        gb = gb or gbuf
-        st = st or stream
-        if ev:
-            ev[0].record(st)
-        api.dp_device(scenes_d, dp, NE, plans=gb.mine)
-        if ev:
-            ev[1].record(st)
-        if use_p2p:
-            api.plan_device_p2p_qp(scenes_d, qp, NE, gb.mine, gb.peer_array, gb.n_peers)   # QP + peer stores
-        else:
-            api.qp_device(scenes_d, qp, NE, gb.mine)
-        if ev:
-            ev[2].record(st)
-        if world > 1:
-            if use_p2p:
-                gb.fence()                                             # 1-element all-reduce = cross-rank barrier
-            else:
-                gb.all_gather()                                        # one in-place NCCL all-gather of plan records
-        if ev:
-            ev[3].record(st)
-
-    for _ in range(args.warmup):
-        step()
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize()
+    wl = SlWorkload(torch, dist, api, sharding, lat, config_id, B, rank, world, dev, args.gather, P, args.flush)
 
     sampler = ClockSampler(local)
     sampler.start()
-    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(args.steps)]
-    for k in range(args.steps):
-        if flush is not None:
-            flush.fill_(k & 0xFF)                                      # evict L2 (126 MB) between timed steps
-        step(evs[k])
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize()
+    times = wl.timed(K, args.warmup, args.min_seconds)                 # the timed regions of `value`
     clocks = sampler.stop()
+    seg = wl.serial(K)                                                 # per-kernel events, one step at a time
+    gather_ok = wl.verify_gather()
+    med = float(np.median(times))
+    value = B * world * K / (med * 1e-3)
+    t_order, t_dp, t_qp, t_coll, t_ser = seg
 
-    t_dp = sum(e[0].elapsed_time(e[1]) for e in evs)
-    t_qp = sum(e[1].elapsed_time(e[2]) for e in evs)
-    t_ser = sum(e[0].elapsed_time(e[3]) for e in evs)                  # ms over the K serial steps
+    if world == 1:
+        e_times, h2d, d2h, e_api = e2e_single(api, wl, K, args.warmup, args.min_seconds, local)
+    else:
+        e_times, h2d, d2h, e_api = e2e_multi(torch, wl, K, args.warmup, args.min_seconds)
+        gather_ok = gather_ok and wl.verify_gather()
+    e_med = float(np.median(e_times))
+    e2e_val = B * world * K / e_med
 
-    # ---- the timed region of `value`: exactly K steps, P batches in flight ------------------
-    # Step k runs on stream k % P with its own plan/gather buffer, so step k+1's DP kernel overlaps step k's QP
-    # kernel (each kernel alone leaves the SMs half idle in its tail: profiles/).  One start and one end event on
-    # the launching stream bracket the region; the L2 flush stays inside it.
-    t_pipe = t_ser
-    if P > 1:
-        streams = [torch.cuda.Stream(device=dev) for _ in range(P)]
-        for k in range(P):
-            with torch.cuda.stream(streams[k]):
-                step(gb=gbufs[k], st=streams[k])
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-        sampler2 = ClockSampler(local)
-        sampler2.start()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(stream)
-        for st_ in streams:
-            st_.wait_event(e0)
-        for k in range(args.steps):
-            st_ = streams[k % P]
-            with torch.cuda.stream(st_):
-                if flush is not None:
-                    flush.fill_(k & 0xFF)
-                step(gb=gbufs[k % P], st=st_)
-        for st_ in streams:
-            stream.wait_stream(st_)
-        e1.record(stream)
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-        clocks = sampler2.stop()
-        t_pipe = e0.elapsed_time(e1)
-    tt = torch.tensor([t_pipe, t_dp, t_qp, t_ser], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-    t_all, t_dp, t_qp, t_ser = [float(v) for v in tt.tolist()]
-    value = B * world * args.steps / (t_all * 1e-3)
-    value_serial = B * world * args.steps / (t_ser * 1e-3)
-
-    # ---- end-to-end through the host-buffer C ABI (what a drop-in caller gets) --------------
-    planner = api.HostPlanner(max_batch=B, kmax=8, n_enr_max=NE, max_col=lat.col, device=local)
-    outs = [api.pinned_empty((B, stride)) for _ in range(P)]         # page-locked host buffers, like a real ingest path
-    recs = [api.pinned_empty(rec_host.shape) for _ in range(P)]
-    for r in recs:
-        r[:] = rec_host
-    rec_host, out = recs[0], outs[0]
-
-    def e2e_steps(n):
-        if P == 1:
-            for _ in range(n):
-                planner.plan(rec_host, dp, qp, out=out)
-            return
-        for k in range(n):                                             # every step: H2D of its scenes, D2H of its plans
-            if k >= P:
-                planner.plan_wait(k % P)
-            planner.plan_submit(k % P, recs[k % P], dp, qp, outs[k % P])
-        for k in range(P):
-            planner.plan_wait(k)
-
-    e2e_steps(args.warmup)
-    if world > 1:
-        dist.barrier()
-    t0 = time.perf_counter()
-    e2e_steps(args.steps)
-    e2e_s = time.perf_counter() - t0
-    e2e_t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
-    e2e_val = B * world * args.steps / float(e2e_t.item())
-    planner.close()
+    extra = {}
+    if not args.no_extras:
+        extra["config2"] = extra_config2(torch, dist, api, sharding, lat, rank, world, dev, args.gather, P, K,
+                                         args.min_seconds / 2)
+        extra["config4"] = extra_config4(torch, dist, api, lat, rank, world, dev, max(2, K // 4), args.min_seconds / 2)
 
     if rank != 0:
+        wl.close()
         if world > 1:
             dist.destroy_process_group()
         return
 
-    view = api.PlanView(mine.cpu().numpy(), NE)
+    view = api.PlanView(wl.gbufs[0].mine.cpu().numpy(), wl.NE)
     n_enr = float(view.n_enr.mean())
     n_qp = float(view.n_qp.mean())
     iters = float(view.qp_iters.mean())
@@ -394,79 +617,89 @@ def main():
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
     peak_src = "MEASURED_PEAKS.json hbm_gbs" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
     dom = "sl_qp_kernel" if t_qp >= t_dp else "sl_dp_kernel"
-    dom_ms = max(t_qp, t_dp) / args.steps
+    dom_ms = max(t_qp, t_dp) / K
     dom_bytes = (b_qp if t_qp >= t_dp else b_dp) * B
     achieved = dom_bytes / (dom_ms * 1e-3) / 1e9
     fp64_tf, _ = api.fp64_peak(8192)
-    # Reference-equivalent FP64 work (SURVEY.md §8(d) operation counts of the *reference* algorithm) per second.
-    # It can exceed the FMA peak: the kernels skip work the reference performs (obstacle culling, closed-form
-    # quintics, a banded instead of dense KKT solve).  The roofline fraction that bounds the kernels is the FP64
-    # pipe utilisation measured by ncu (profiles/, static per round), not this number.
-    ref_flops = (dp_flops(lat, float(shard["nobs"].mean())) + 25e6) * B      # DP + dense-cvxopt QP (~25 MFLOP, §8(d))
-    ref_equiv = ref_flops / (t_all / args.steps * 1e-3) / 1e12
-    ncu = NCU_STATIC.get(lat.name, {})
+    ref_flops = (dp_flops(lat, float(wl.shard["nobs"].mean())) + 25e6) * B      # DP + dense-cvxopt QP (~25 MFLOP, 8(d))
+    ref_equiv = ref_flops / (med / K * 1e-3) / 1e12
+    ncu, ncu_src = ncu_facts()
+    nk = (ncu or {}).get("kernels", {})
 
     cpu = None
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and world == 1:
         cores = host_cores()
-        per_core = max(2, args.cpu_frames // cores)
-        v, f, wall, dp_share = cpu_port_throughput(args.lattice, config_id, per_core, cores)
+        frames = args.cpu_frames if args.cpu_frames > 0 else 1024
+        v, f, wall, dp_share = cpu_port_throughput(args.lattice, config_id, frames, cores, B)
         cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
-               "sample": "%d-frame prefix of the batch (%d per core), numpy float64 oracle port of DP->corridor->QP, "
-                         "%.1f s wall, DP share of CPU time %.0f%%" % (f, per_core, wall, 100 * dp_share)}
-
-    if cpu:
-        # the unmodified reference's own DP time per frame, recorded while the golden fixtures were generated in the
-        # build container (the reference is Python that cannot travel to the GPU box): context, not a measurement here
+               "sample": "%d-frame prefix of the batch, numpy float64 oracle port of DP->corridor->QP (same stopping rule as "
+                         "the kernels), %d processes, %.1f s wall, DP share of CPU time %.0f%%" % (f, cores, wall, 100 * dp_share)}
         try:
             gsec = np.load(os.path.join(ROOT, "tests", "golden", "sl_%s.npz" % args.lattice))["ref_dp_seconds"]
             cpu["reference_python"] = {"dp_seconds_per_frame_one_core": float(np.mean(gsec)), "frames": int(len(gsec)),
-                                       "where": "build container, tests/golden/sl_%s.npz:ref_dp_seconds "
-                                                "(DP_algorithm only; its QP needs cvxopt)" % args.lattice}
+                                       "where": "build container, tests/golden/sl_%s.npz:ref_dp_seconds (the unmodified "
+                                                "reference's DP_algorithm only; its QP needs cvxopt)" % args.lattice}
         except Exception:
             pass
 
+    if args.flush:
+        l2_note = "flushed with a 256 MiB write before every step (inside the timed region)"
+    else:
+        l2_note = ("steps rotate over %d scene/plan buffer sets = %.0f MB > 2 x %.0f MB L2: every step touches memory "
+                   "evicted since its last use; no flush kernel in the timed region" % (
+                       wl.NB, wl.NB * wl.set_bytes / 1e6, wl.l2_bytes / 1e6))
+    workload = workload_string(B, lat)
+    gather_note = None
+    if world > 1:
+        gather_note = ("all-gather of plan records fused into the QP kernel (P2P stores over NVLink + arrival flags + "
+                       "credits, no collective)" if wl.p2p else "one NCCL all-gather of plan records per step")
     line = {
-        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": t_all / args.steps, "higher_is_better": True,
-        "pipeline": {"batches_in_flight": P, "value_serial_steps": value_serial, "ms_per_serial_step": t_ser / args.steps,
-                     "note": "value: step k+1's DP kernel overlaps step k's QP kernel (stream k % P, own plan buffer); "
-                             "kernels_ms / roofline: the serial pass, one kernel at a time"}, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "batch=%d/GPU synthetic Frenet scenes, %dx%d S-L lattice (%s), 0-8 random obstacles, "
-                               "DP->[::2]->corridor->QP%s" % (B, lat.col, lat.row, lat.name,
-                                                               (", all-gather of plan records fused into the QP kernel "
-                                                                "(P2P stores over NVLink)" if use_p2p else
-                                                                ", NCCL all-gather of plan records") if world > 1 else ""),
-                   "lattice": lat.name, "batch_per_gpu": B, "global_batch": B * world,
-                   "parallelism": "frame-sharded x%d" % world,
-                   "l2": "flushed with a 256 MiB write between timed steps" if flush is not None else "not flushed",
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": args.warmup,
+        "ms_per_step": med / K, "higher_is_better": True,
+        "regions": {"count": len(times), "median_ms": med, "min_ms": float(min(times)), "max_ms": float(max(times)),
+                    "timed_total_s": float(sum(times)) * 1e-3,
+                    "note": "each region = exactly `steps` steps between barrier + synchronize, max over ranks; value and "
+                            "ms_per_step are the median region's"},
+        "pipeline": {"batches_in_flight": P, "value_serial_steps": B * world * K / (t_ser * 1e-3),
+                     "ms_per_serial_step": t_ser / K,
+                     "note": "value: step k+1's DP kernel overlaps step k's QP kernel (stream k % P, own buffers); "
+                             "kernels_ms / roofline: the serial pass, one kernel at a time"},
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": workload, "lattice": lat.name, "batch_per_gpu": B, "global_batch": B * world,
+                   "parallelism": "frame-sharded x%d" % world, "gather": gather_note, "l2": l2_note,
                    "qp_optimal_fraction": frac_opt, "qp_mean_iterations": iters, "qp_iterations": it_stats},
-        "kernels_ms": {"sl_dp_kernel": t_dp / args.steps, "sl_qp_kernel": t_qp / args.steps,
-                       "collective": max(t_ser - t_dp - t_qp, 0.0) / args.steps},
+        "kernels_ms": {"sl_order_kernel": t_order / K, "sl_dp_kernel": t_dp / K, "sl_qp_kernel": t_qp / K,
+                       "collective": t_coll / K},
         "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
-                     "frac": achieved / hbm_peak, "traffic": ncu.get("dram_bytes_per_launch", {}).get(dom),
+                     "frac": achieved / hbm_peak, "traffic": nk.get(dom, {}).get("dram_bytes_per_launch"),
                      "peak_source": peak_src,
                      "algorithmic_bytes_per_frame": (b_qp if t_qp >= t_dp else b_dp),
-                     "note": "path is FP64-latency bound, not HBM bound (SURVEY.md §0.5); see compute"},
+                     "note": "path is FP64-latency bound, not HBM bound (SURVEY.md 0.5); see compute"},
         "compute": {"bound": "fp64", "kernel": dom, "peak": fp64_tf, "unit": "TFLOP/s",
                     "peak_source": "emp_fp64_peak FMA micro-benchmark, this GPU, this run",
-                    "fp64_pipe_active_frac": ncu.get("fp64_pipe_active"), "issue_active_frac": ncu.get("issue_active"),
-                    "ncu_source": ncu.get("source"),
-                    "reference_equivalent_tflops": ref_equiv,
-                    "note": "fraction of the FP64 roofline = ncu sm__pipe_fp64_cycles_active of the dominant kernel; "
-                            "reference_equivalent counts the reference's operation count and may exceed the peak"},
-        "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": int(rec_host.nbytes),
-                "d2h_bytes_per_step": int(out.nbytes), "api": ("emp_sl_plan_submit/emp_sl_plan_wait via HostPlanner.plan_submit, %d slots, " % P if P > 1 else
-                        "emp_sl_plan_host via HostPlanner.plan, ") + "page-locked host buffers"},
-        "gpu_launches": 2 * args.steps, "collectives": (args.steps if world > 1 else 0),
+                    "fp64_pipe_active_frac": {k: v.get("fp64_pipe_active") for k, v in nk.items()} or None,
+                    "issue_active_frac": {k: v.get("issue_active") for k, v in nk.items()} or None,
+                    "ncu_source": ncu_src, "reference_equivalent_tflops": ref_equiv,
+                    "note": "fraction of the FP64 roofline = ncu sm__pipe_fp64_cycles_active of the dominant kernel (one "
+                            "capture per kernel change, keyed by source hash); reference_equivalent counts the reference's "
+                            "operation count and may exceed the peak"},
+        "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "api": e_api,
+                "regions": len(e_times), "min_s": float(min(e_times)), "max_s": float(max(e_times))},
+        "gpu_launches": wl.launches_per_step * K, "collectives": (K if world > 1 and not wl.p2p else 0),
         "clocks": clocks,
     }
+    if world > 1:
+        line["gather_verified"] = gather_ok
+    if extra:
+        line["extra"] = extra
     if cpu:
         line["cpu_baseline"] = cpu
     print(json.dumps(line), flush=True)
+    wl.close()
     if world > 1:
         dist.destroy_process_group()
+    if world > 1 and not gather_ok:
+        raise SystemExit("gathered plan records differ from the NCCL all-gather of the same records")
 
 
 if __name__ == "__main__":

@@ -44,7 +44,7 @@ class SpeedQpParams(C.Structure):
     """EmpSpeedQpParams: speed_QP / generate_convex_space keyword defaults (speed_planning_test.py:403-404, :309)."""
     _fields_ = [("w_s_dot2", C.c_double), ("w_v_ref", C.c_double), ("w_jerk", C.c_double),
                 ("reference_speed", C.c_double), ("max_lateral_accel", C.c_double), ("abstol", C.c_double),
-                ("reltol", C.c_double), ("feastol", C.c_double), ("maxiters", C.c_int32), ("reserved", C.c_int32),
+                ("reltol", C.c_double), ("feastol", C.c_double), ("maxiters", C.c_int32), ("repair_full_profile", C.c_int32),
                 ("diverge_factor", C.c_double)]
 
 
@@ -68,11 +68,12 @@ _SIGNATURES = {
     "emp_max_enriched": (C.c_int, [_DPP]),
     "emp_version": (C.c_int, []),
     "emp_last_error": (C.c_char_p, []),
-    "emp_sl_dp_dev": (C.c_int, [_P, C.c_int, C.c_int, _DPP, C.c_int, _P, _P, _P]),
-    "emp_sl_qp_dev": (C.c_int, [_P, C.c_int, C.c_int, _QPP, C.c_int, _P, _P, _P]),
+    "emp_sl_order_dev": (C.c_int, [_P, C.c_int, C.c_int, _P, _P]),
+    "emp_sl_dp_dev": (C.c_int, [_P, C.c_int, C.c_int, _DPP, C.c_int, _P, _P, _P, _P]),
+    "emp_sl_qp_dev": (C.c_int, [_P, C.c_int, C.c_int, _QPP, C.c_int, _P, _P, _P, _P]),
     "emp_qp_dev": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, _QPP, _P, _P, _P]),
     "emp_corridor_dev": (C.c_int, [_P, _P, C.c_int, _P, C.c_int, C.c_int, _QPP, _P, _P, _P]),
-    "emp_sl_plan_dev": (C.c_int, [_P, C.c_int, C.c_int, _DPP, _QPP, C.c_int, _P, _P, _P]),
+    "emp_sl_plan_dev": (C.c_int, [_P, C.c_int, C.c_int, _DPP, _QPP, C.c_int, _P, _P, _P, _P]),
     "emp_frenet_project_dev": (C.c_int, [_P, C.c_int, _P, _P, _P, C.c_int, _P, _P, _P, _P, C.c_int, _P, _P, _P, _P, _P, _P]),
     "emp_frenet_to_cart_dev": (C.c_int, [_P, _P, C.c_int, _P, _P, _P, _P, C.c_int, C.c_int, _P, _P, _P]),
     "emp_frenet_project_host": (C.c_int, [_P, _P, C.c_int, _P, _P, _P, C.c_int, _P, _P, _P, _P, C.c_int, _P, _P, _P, _P, _P]),
@@ -90,7 +91,7 @@ _SIGNATURES = {
     "emp_st_path_speed_merge_dev": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, _P, _P, _P]),
     "emp_st_back_host": (C.c_int, [_P, C.c_int, C.POINTER(SpeedQpParams), _P, _P, C.c_int, _P, C.c_int, _P, _P, _P, _P,
                                    _P, _P, C.c_int, _P, _P, _P, _P, _P, _P, _P, _P]),
-    "emp_cycle_path_points_dev": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, _P, _P, _P]),
+    "emp_cycle_path_points_dev": (C.c_int, [_P, C.c_int, _P, C.c_int, C.c_int, C.c_int, _P, _P, _P]),
     "emp_cycle_path_tables_dev": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, _P, _P, _P]),
     "emp_fp64_peak": (C.c_int, [C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "emp_planner_create": (C.c_int, [C.POINTER(_P), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),
@@ -101,8 +102,10 @@ _SIGNATURES = {
     "emp_sl_dp_host": (C.c_int, [_P, _P, C.c_int, _DPP, _P, _P]),
     "emp_qp_host": (C.c_int, [_P, _P, _P, _P, C.c_int, C.c_int, _QPP, _P, _P]),
     "emp_corridor_host": (C.c_int, [_P, _P, _P, C.c_int, _P, C.c_int, _QPP, _P, _P]),
-    "emp_sl_plan_p2p_dev": (C.c_int, [_P, C.c_int, C.c_int, _DPP, _QPP, C.c_int, _P, _P, C.c_int, _P, _P]),
-    "emp_sl_qp_p2p_dev": (C.c_int, [_P, C.c_int, C.c_int, _QPP, C.c_int, _P, C.c_int, _P, _P]),
+    "emp_sl_plan_p2p_dev": (C.c_int, [_P, C.c_int, C.c_int, _DPP, _QPP, C.c_int, _P, _P, C.c_int, _P, _P, _P]),
+    "emp_sl_qp_p2p_dev": (C.c_int, [_P, C.c_int, C.c_int, _QPP, C.c_int, _P, C.c_int, _P, _P, _P]),
+    "emp_sl_qp_gather_dev": (C.c_int, [_P, C.c_int, C.c_int, _QPP, C.c_int, _P, C.c_int, _P, C.c_uint64, _P, _P, _P, _P]),
+    "emp_gather_wait_signal_dev": (C.c_int, [_P, C.c_int, C.c_uint64, _P, C.c_int, _P, C.c_int, _P]),
     "emp_device_alloc": (_P, [C.c_size_t]),
     "emp_device_free": (None, [_P]),
     "emp_ipc_export": (C.c_int, [_P, _P]),
@@ -188,12 +191,13 @@ def st_params(reference_speed=50, w_cost_ref_speed=4000, w_cost_accel=100, w_cos
 
 def speed_qp_params(w_cost_s_dot2=10, w_cost_v_ref=50, w_cost_jerk=500, reference_speed=50,
                     max_lateral_accel=0.2 * 9.8, abstol=1e-7, reltol=1e-6, feastol=1e-7, maxiters=100,
-                    diverge_factor=2.0):
+                    diverge_factor=100.0, repair_full_profile=False):
     p = SpeedQpParams()
     p.w_s_dot2, p.w_v_ref, p.w_jerk = float(w_cost_s_dot2), float(w_cost_v_ref), float(w_cost_jerk)
     p.reference_speed, p.max_lateral_accel = float(reference_speed), float(max_lateral_accel)
     p.abstol, p.reltol, p.feastol, p.maxiters = float(abstol), float(reltol), float(feastol), int(maxiters)
     p.diverge_factor = float(diverge_factor or 0.0)
+    p.repair_full_profile = 1 if repair_full_profile else 0
     return p
 
 

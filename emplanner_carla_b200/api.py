@@ -430,9 +430,21 @@ def _stream_ptr():
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
-def plan_device(scenes, dp, qp, n_enr_max, plans=None, rows=None, kmax=None):
+def order_device(scenes, order=None):
+    """Schedule for the two S-L kernels (emp_sl_order_dev): frame indices by obstacle count, descending."""
+    import torch
+    B = scenes.shape[0]
+    kmax = (scenes.shape[1] - SCENE_HDR) // 2
+    if order is None:
+        order = torch.empty(B, dtype=torch.int32, device=scenes.device)
+    _lib.check(_lib.lib().emp_sl_order_dev(_dev_ptr(scenes), kmax, B, _dev_ptr(order), _stream_ptr()))
+    return order
+
+
+def plan_device(scenes, dp, qp, n_enr_max, plans=None, rows=None, kmax=None, order_ws=None):
     """S-L planning step on device tensors: scenes [B, 6+2*kmax] f64 cuda -> plans [B, stride] f64 cuda.
-    Enqueues two kernels on torch's current stream and returns immediately."""
+    Enqueues the kernels on torch's current stream and returns immediately.  order_ws: optional [B] int32 CUDA
+    tensor; when given, the launch-balancing schedule (order_device) is computed into it and followed."""
     import torch
     if not scenes.is_cuda or scenes.dtype != torch.float64 or not scenes.is_contiguous():
         raise ValueError("scenes must be a contiguous float64 CUDA tensor")
@@ -441,45 +453,46 @@ def plan_device(scenes, dp, qp, n_enr_max, plans=None, rows=None, kmax=None):
     if plans is None:
         plans = torch.empty((B, plan_stride(n_enr_max)), dtype=torch.float64, device=scenes.device)
     _lib.check(_lib.lib().emp_sl_plan_dev(_dev_ptr(scenes), kmax, B, C.byref(dp), C.byref(qp), int(n_enr_max),
-                                          _dev_ptr(plans), _dev_ptr(rows), _stream_ptr()))
+                                          _dev_ptr(plans), _dev_ptr(rows), _dev_ptr(order_ws), _stream_ptr()))
     return plans
 
 
-def plan_device_p2p(scenes, dp, qp, n_enr_max, plans, peer_array, n_peers, rows=None):
+def plan_device_p2p(scenes, dp, qp, n_enr_max, plans, peer_array, n_peers, rows=None, order_ws=None):
     """plan_device + fused all-gather: each finished plan record is also stored into the peers' gather buffers
     (peer_array: ctypes array of device pointers from sharding.PeerGatherBuffer)."""
     B = scenes.shape[0]
     kmax = (scenes.shape[1] - SCENE_HDR) // 2
     _lib.check(_lib.lib().emp_sl_plan_p2p_dev(_dev_ptr(scenes), kmax, B, C.byref(dp), C.byref(qp), int(n_enr_max),
-                                              _dev_ptr(plans), _dev_ptr(rows), int(n_peers), peer_array, _stream_ptr()))
+                                              _dev_ptr(plans), _dev_ptr(rows), int(n_peers), peer_array,
+                                              _dev_ptr(order_ws), _stream_ptr()))
     return plans
 
 
-def plan_device_p2p_qp(scenes, qp, n_enr_max, plans, peer_array, n_peers):
+def plan_device_p2p_qp(scenes, qp, n_enr_max, plans, peer_array, n_peers, order=None):
     """The corridor+QP launch of the fused step (after dp_device), with peer stores."""
     B = scenes.shape[0]
     kmax = (scenes.shape[1] - SCENE_HDR) // 2
     _lib.check(_lib.lib().emp_sl_qp_p2p_dev(_dev_ptr(scenes), kmax, B, C.byref(qp), int(n_enr_max), _dev_ptr(plans),
-                                            int(n_peers), peer_array, _stream_ptr()))
+                                            int(n_peers), peer_array, _dev_ptr(order), _stream_ptr()))
     return plans
 
 
-def dp_device(scenes, dp, n_enr_max, plans=None, rows=None):
+def dp_device(scenes, dp, n_enr_max, plans=None, rows=None, order=None):
     import torch
     B = scenes.shape[0]
     kmax = (scenes.shape[1] - SCENE_HDR) // 2
     if plans is None:
         plans = torch.zeros((B, plan_stride(n_enr_max)), dtype=torch.float64, device=scenes.device)
     _lib.check(_lib.lib().emp_sl_dp_dev(_dev_ptr(scenes), kmax, B, C.byref(dp), int(n_enr_max), _dev_ptr(plans),
-                                        _dev_ptr(rows), _stream_ptr()))
+                                        _dev_ptr(rows), _dev_ptr(order), _stream_ptr()))
     return plans
 
 
-def qp_device(scenes, qp, n_enr_max, plans, lmin_lmax=None):
+def qp_device(scenes, qp, n_enr_max, plans, lmin_lmax=None, order=None):
     B = scenes.shape[0]
     kmax = (scenes.shape[1] - SCENE_HDR) // 2
     _lib.check(_lib.lib().emp_sl_qp_dev(_dev_ptr(scenes), kmax, B, C.byref(qp), int(n_enr_max), _dev_ptr(plans),
-                                        _dev_ptr(lmin_lmax), _stream_ptr()))
+                                        _dev_ptr(lmin_lmax), _dev_ptr(order), _stream_ptr()))
     return plans
 
 
@@ -519,16 +532,17 @@ class EmCycle:
         S-L DP -> [::2] -> corridor -> QP -> mid-point path (test_9.py:204-210) -> smooth_reference_line (QP#3)
         + cal_heading_kappa -> trajectory_index2s -> S-T DP -> generate_convex_space -> speed QP
         -> increase_points -> path_speed_merge.
-    Eleven launches on torch's current stream, no host round trip; torch tensors only hold the device buffers.
-    The batched cycle plans along the s-axis (no per-scene reference line among configs[4]'s inputs), for which
-    frenet_2_x_y_theta_kappa's projection is the identity."""
+    Eleven launches (N_LAUNCHES) on torch's current stream, no host round trip; torch tensors only hold the device
+    buffers.  The batched cycle plans along the s-axis (no per-scene reference line among configs[4]'s inputs), for
+    which frenet_2_x_y_theta_kappa's projection is the identity; like that function the path handed to the smoother
+    starts with the plan-start point (path_planning.py:31-34)."""
 
     def __init__(self, batch, dp, qp, st, sq, sm, sl_kmax=8, st_kmax=8, device=None):
         import torch
         self.B, self.dp, self.qp, self.st, self.sq, self.sm = int(batch), dp, qp, st, sq, sm
         self.sl_kmax, self.st_kmax = int(sl_kmax), int(st_kmax)
         self.NE = max_enriched(dp)
-        self.MP = (self.NE + 1) // 2 + 1                  # mid-point path: n_qp + 1 points
+        self.MP = (self.NE + 1) // 2 + 2                  # plan start + mid-point path: n_qp + 2 points (path_planning.py:31-34)
         if self.MP > 64:
             raise ValueError("path of %d points exceeds the 64 points of the reference-line smoother" % self.MP)
         self.NP = self.MP + 1                             # + NaN terminator (speed_planning_test.py:581)
@@ -536,7 +550,7 @@ class EmCycle:
         f64 = lambda *s: torch.zeros(s, dtype=torch.float64, device=dev)
         i32 = lambda *s: torch.zeros(s, dtype=torch.int32, device=dev)
         B = self.B
-        self.buf = dict(plans=f64(B, plan_stride(self.NE)), xy=f64(B, self.MP, 2), npts=i32(B), cart=f64(B, self.MP, 4),
+        self.buf = dict(plans=f64(B, plan_stride(self.NE)), order=i32(B), xy=f64(B, self.MP, 2), npts=i32(B), cart=f64(B, self.MP, 4),
                         smooth_status_iters=i32(B, 2), path2=f64(B, 2, self.NP), path5=f64(B, 5, self.NP),
                         st_out=f64(B, ST_OUT_STRIDE), bounds=f64(B, 4, ST_COLS), convex_status=i32(B),
                         qp=f64(B, 4, ST_QP_POINTS), qp_status_iters=i32(B, 2), dense=f64(B, 4, ST_DENSE),
@@ -550,9 +564,10 @@ class EmCycle:
         ck = _lib.check
         mark = mark or (lambda name: None)
         ck(L.emp_sl_plan_dev(p(sl_scenes), self.sl_kmax, B, C.byref(self.dp), C.byref(self.qp), self.NE, p(b["plans"]),
-                             None, sp))
+                             None, p(b["order"]), sp))
         mark("sl_dp+sl_qp")
-        ck(L.emp_cycle_path_points_dev(p(b["plans"]), self.NE, B, self.MP, p(b["xy"]), p(b["npts"]), sp))
+        ck(L.emp_cycle_path_points_dev(p(b["plans"]), self.NE, p(sl_scenes), self.sl_kmax, B, self.MP, p(b["xy"]),
+                                       p(b["npts"]), sp))
         ck(L.emp_smooth_line_dev(p(b["xy"]), p(b["npts"]), self.MP, B, C.byref(self.sm), p(b["cart"]),
                                  p(b["smooth_status_iters"]), sp))
         ck(L.emp_cycle_path_tables_dev(p(b["cart"]), p(b["npts"]), self.MP, B, self.NP, p(b["path2"]), p(b["path5"]), sp))
@@ -570,4 +585,4 @@ class EmCycle:
         mark("increase_points + path_speed_merge")
         return b
 
-    N_LAUNCHES = 10
+    N_LAUNCHES = 11                                       # schedule, DP, QP, 2 x glue, smoother, S-T DP, convex space, speed QP, densify, merge

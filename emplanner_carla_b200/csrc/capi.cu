@@ -61,6 +61,7 @@ int make_dp_launch(emp::DpLaunch &L, const EmpDpParams *p, int kmax, int batch, 
     L.scene_stride = emp_scene_stride(kmax);
     L.plan_stride = emp_plan_stride(n_enr_max);
     L.batch = batch;
+    L.order = nullptr;
     const int RR = L.R * L.R;
     int off = 16;                                        // mbarrier
     L.off_slab = off;  off += align_up(emp::DP_WARPS * L.scene_stride * 8, 16);
@@ -97,8 +98,11 @@ int make_qp_launch(emp::QpLaunch &L, const EmpQpParams *p, int kmax, int batch, 
     L.n_enr_max = n_enr_max;
     L.n_direct = n_direct;
     L.mode = mode;
+    L.order = nullptr;
     L.n_peers = 0;
-    for (int r = 0; r < EMP_MAX_PEERS; ++r) L.peer[r] = nullptr;
+    L.epoch = 0;
+    L.self_ready = nullptr;
+    for (int r = 0; r < EMP_MAX_PEERS; ++r) { L.peer[r] = nullptr; L.peer_ready[r] = nullptr; }
     return 0;
 }
 
@@ -136,15 +140,16 @@ struct EmpPlanner {
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     double *d_scenes = nullptr, *d_plans = nullptr, *d_qp_in = nullptr, *d_qp_out = nullptr;
-    int32_t *d_rows = nullptr, *d_status = nullptr;
+    int32_t *d_rows = nullptr, *d_status = nullptr, *d_order = nullptr;
     double *h_scenes = nullptr, *h_plans = nullptr;       // pinned staging
     int32_t *h_rows = nullptr;
     float last_ms = 0.f;
-    // pipelined planning (emp_sl_plan_submit / emp_sl_plan_wait): slot 0 reuses the buffers above
+    // pipelined planning (emp_sl_plan_submit / emp_sl_plan_wait): every slot has its own stream and device buffers,
+    // none shared with the synchronous entry points above (which run on `stream`)
     struct Slot {
         cudaStream_t stream = nullptr;
         double *d_scenes = nullptr, *d_plans = nullptr;
-        int32_t *d_rows = nullptr;
+        int32_t *d_rows = nullptr, *d_order = nullptr;
         bool busy = false;
     } slot[EMP_PLAN_SLOTS];
 };
@@ -159,8 +164,8 @@ void emp_smooth_params_default(EmpSmoothParams *p) {
 
 void emp_speed_qp_params_default(EmpSpeedQpParams *p) {
     p->w_s_dot2 = 10; p->w_v_ref = 50; p->w_jerk = 500; p->reference_speed = 50; p->max_lateral_accel = 0.2 * 9.8;
-    p->abstol = 1e-7; p->reltol = 1e-6; p->feastol = 1e-7; p->maxiters = 100; p->reserved = 0;
-    p->diverge_factor = 2.0;
+    p->abstol = 1e-7; p->reltol = 1e-6; p->feastol = 1e-7; p->maxiters = 100; p->repair_full_profile = 0;
+    p->diverge_factor = 100.0;
 }
 
 void emp_st_params_default(EmpStParams *p) {
@@ -199,22 +204,33 @@ int emp_max_enriched(const EmpDpParams *p) {
 int emp_version(void) { return EMP_VERSION; }
 const char *emp_last_error(void) { return g_err; }
 
+int emp_sl_order_dev(const double *scenes, int kmax, int batch, int32_t *order, void *stream) {
+    if (kmax < 0 || kmax > EMP_MAX_KMAX || (kmax & 1)) return fail(-2, "kmax must be even and in [0, 32]");
+    if (batch < 0) return fail(-2, "bad batch");
+    if (batch == 0) return 0;
+    if (!scenes || !order) return fail(-1, "scenes/order is NULL");
+    cudaError_t e = emp::launch_sl_order(scenes, emp_scene_stride(kmax), kmax, batch, order, (cudaStream_t)stream);
+    return e == cudaSuccess ? 0 : fail_cuda(e, "sl_order launch");
+}
+
 int emp_sl_dp_dev(const double *scenes, int kmax, int batch, const EmpDpParams *p, int n_enr_max,
-                  double *plans, int32_t *rows, void *stream) {
+                  double *plans, int32_t *rows, const int32_t *order, void *stream) {
     emp::DpLaunch L;
     if (int rc = make_dp_launch(L, p, kmax, batch, n_enr_max)) return rc;
     if (batch == 0) return 0;
     if (!scenes || !plans) return fail(-1, "scenes/plans is NULL");
+    L.order = order;
     cudaError_t e = emp::launch_sl_dp(scenes, plans, rows, L, (cudaStream_t)stream);
     return e == cudaSuccess ? 0 : fail_cuda(e, "sl_dp launch");
 }
 
 int emp_sl_qp_dev(const double *scenes, int kmax, int batch, const EmpQpParams *p, int n_enr_max,
-                  double *plans, double *lmin_lmax, void *stream) {
+                  double *plans, double *lmin_lmax, const int32_t *order, void *stream) {
     emp::QpLaunch L;
     if (int rc = make_qp_launch(L, p, kmax, batch, n_enr_max, 0, emp::QP_MODE_FUSED)) return rc;
     if (batch == 0) return 0;
     if (!scenes || !plans) return fail(-1, "scenes/plans is NULL");
+    L.order = order;
     cudaError_t e = emp::launch_sl_qp(scenes, plans, lmin_lmax, nullptr, nullptr, nullptr, nullptr, nullptr, L,
                                       (cudaStream_t)stream);
     return e == cudaSuccess ? 0 : fail_cuda(e, "sl_qp launch");
@@ -245,9 +261,11 @@ int emp_corridor_dev(const double *dp_s, const double *dp_l, int n, const double
 }
 
 int emp_sl_plan_dev(const double *scenes, int kmax, int batch, const EmpDpParams *dp, const EmpQpParams *qp,
-                    int n_enr_max, double *plans, int32_t *rows, void *stream) {
-    if (int rc = emp_sl_dp_dev(scenes, kmax, batch, dp, n_enr_max, plans, rows, stream)) return rc;
-    return emp_sl_qp_dev(scenes, kmax, batch, qp, n_enr_max, plans, nullptr, stream);
+                    int n_enr_max, double *plans, int32_t *rows, int32_t *order_ws, void *stream) {
+    if (order_ws)
+        if (int rc = emp_sl_order_dev(scenes, kmax, batch, order_ws, stream)) return rc;
+    if (int rc = emp_sl_dp_dev(scenes, kmax, batch, dp, n_enr_max, plans, rows, order_ws, stream)) return rc;
+    return emp_sl_qp_dev(scenes, kmax, batch, qp, n_enr_max, plans, nullptr, order_ws, stream);
 }
 
 int emp_frenet_project_dev(const double *lines, int n_nodes, const double *origin, const double *points,
@@ -307,7 +325,7 @@ int emp_st_dp_dev(const double *scenes, int kmax, int batch, const EmpStParams *
 }
 
 int emp_sl_qp_p2p_dev(const double *scenes, int kmax, int batch, const EmpQpParams *qp, int n_enr_max,
-                      double *plans, int n_peers, double *const *peer_slices, void *stream) {
+                      double *plans, int n_peers, double *const *peer_slices, const int32_t *order, void *stream) {
     if (n_peers < 0 || n_peers > EMP_MAX_PEERS) return fail(-2, "n_peers must be in [0, 8]");
     if (n_peers > 0 && !peer_slices) return fail(-1, "peer_slices is NULL");
     emp::QpLaunch L;
@@ -315,6 +333,7 @@ int emp_sl_qp_p2p_dev(const double *scenes, int kmax, int batch, const EmpQpPara
     if (batch == 0) return 0;
     if (!scenes || !plans) return fail(-1, "scenes/plans is NULL");
     L.n_peers = n_peers;
+    L.order = order;
     for (int r = 0; r < n_peers; ++r) {
         if (!peer_slices[r]) return fail(-1, "peer slice is NULL");
         L.peer[r] = peer_slices[r];
@@ -324,11 +343,48 @@ int emp_sl_qp_p2p_dev(const double *scenes, int kmax, int batch, const EmpQpPara
     return e == cudaSuccess ? 0 : fail_cuda(e, "sl_qp (p2p) launch");
 }
 
+int emp_sl_qp_gather_dev(const double *scenes, int kmax, int batch, const EmpQpParams *qp, int n_enr_max,
+                         double *plans, int n_peers, double *const *peer_slices, uint64_t epoch,
+                         uint64_t *self_ready, uint64_t *const *peer_ready, const int32_t *order, void *stream) {
+    if (n_peers < 0 || n_peers > EMP_MAX_PEERS) return fail(-2, "n_peers must be in [0, 8]");
+    if (n_peers > 0 && (!peer_slices || !peer_ready)) return fail(-1, "peer_slices / peer_ready is NULL");
+    if (epoch == 0 || !self_ready) return fail(-2, "epoch must be > 0 and self_ready not NULL");
+    emp::QpLaunch L;
+    if (int rc = make_qp_launch(L, qp, kmax, batch, n_enr_max, 0, emp::QP_MODE_FUSED)) return rc;
+    if (batch <= 0) return fail(-2, "batch must be > 0 (the arrival flag is written by the launch's last warp)");
+    if (!scenes || !plans) return fail(-1, "scenes/plans is NULL");
+    L.n_peers = n_peers;
+    L.order = order;
+    L.epoch = epoch;
+    L.self_ready = reinterpret_cast<unsigned long long *>(self_ready);
+    for (int r = 0; r < n_peers; ++r) {
+        if (!peer_slices[r] || !peer_ready[r]) return fail(-1, "peer slice / flag is NULL");
+        L.peer[r] = peer_slices[r];
+        L.peer_ready[r] = reinterpret_cast<unsigned long long *>(peer_ready[r]);
+    }
+    cudaError_t e = emp::launch_sl_qp(scenes, plans, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, L,
+                                      (cudaStream_t)stream);
+    return e == cudaSuccess ? 0 : fail_cuda(e, "sl_qp (gather) launch");
+}
+
+int emp_gather_wait_signal_dev(const uint64_t *flags, int n_wait, uint64_t epoch, uint64_t *const *signal,
+                               int n_signal, int32_t *err, int timeout_ms, void *stream) {
+    if (n_wait < 0 || n_wait > 32 || n_signal < 0 || n_signal > EMP_MAX_PEERS + 1) return fail(-2, "bad n_wait / n_signal");
+    if ((n_wait > 0 && !flags) || (n_signal > 0 && !signal)) return fail(-1, "NULL argument");
+    if (timeout_ms <= 0) timeout_ms = 2000;
+    cudaError_t e = emp::launch_flag_wait_signal(reinterpret_cast<const unsigned long long *>(flags), n_wait, epoch,
+                                                 reinterpret_cast<unsigned long long *const *>(signal), n_signal, err,
+                                                 timeout_ms, (cudaStream_t)stream);
+    return e == cudaSuccess ? 0 : fail_cuda(e, "gather wait/signal launch");
+}
+
 int emp_sl_plan_p2p_dev(const double *scenes, int kmax, int batch, const EmpDpParams *dp, const EmpQpParams *qp,
                         int n_enr_max, double *plans, int32_t *rows, int n_peers, double *const *peer_slices,
-                        void *stream) {
-    if (int rc = emp_sl_dp_dev(scenes, kmax, batch, dp, n_enr_max, plans, rows, stream)) return rc;
-    return emp_sl_qp_p2p_dev(scenes, kmax, batch, qp, n_enr_max, plans, n_peers, peer_slices, stream);
+                        int32_t *order_ws, void *stream) {
+    if (order_ws)
+        if (int rc = emp_sl_order_dev(scenes, kmax, batch, order_ws, stream)) return rc;
+    if (int rc = emp_sl_dp_dev(scenes, kmax, batch, dp, n_enr_max, plans, rows, order_ws, stream)) return rc;
+    return emp_sl_qp_p2p_dev(scenes, kmax, batch, qp, n_enr_max, plans, n_peers, peer_slices, order_ws, stream);
 }
 
 void *emp_device_alloc(size_t bytes) {
@@ -406,6 +462,7 @@ int emp_planner_create(EmpPlanner **out, int device, int max_batch, int kmax, in
     ok(cudaMalloc(&pl->d_qp_in, qb));
     ok(cudaMalloc(&pl->d_qp_out, qb));
     ok(cudaMalloc(&pl->d_status, (size_t)max_batch * 2 * 4));
+    ok(cudaMalloc(&pl->d_order, (size_t)max_batch * 4));
     ok(cudaMallocHost(&pl->h_scenes, sb));
     ok(cudaMallocHost(&pl->h_plans, pb));
     ok(cudaMallocHost(&pl->h_rows, rb));
@@ -422,11 +479,11 @@ void emp_planner_destroy(EmpPlanner *pl) {
     cudaSetDevice(pl->device);
     if (pl->stream) cudaStreamSynchronize(pl->stream);
     cudaFree(pl->d_scenes); cudaFree(pl->d_plans); cudaFree(pl->d_rows);
-    cudaFree(pl->d_qp_in); cudaFree(pl->d_qp_out); cudaFree(pl->d_status);
+    cudaFree(pl->d_qp_in); cudaFree(pl->d_qp_out); cudaFree(pl->d_status); cudaFree(pl->d_order);
     cudaFreeHost(pl->h_scenes); cudaFreeHost(pl->h_plans); cudaFreeHost(pl->h_rows);
     for (int k = 0; k < EMP_PLAN_SLOTS; ++k) {
         if (pl->slot[k].stream) { cudaStreamSynchronize(pl->slot[k].stream); cudaStreamDestroy(pl->slot[k].stream); }
-        if (k > 0) { cudaFree(pl->slot[k].d_scenes); cudaFree(pl->slot[k].d_plans); cudaFree(pl->slot[k].d_rows); }
+        cudaFree(pl->slot[k].d_scenes); cudaFree(pl->slot[k].d_plans); cudaFree(pl->slot[k].d_rows); cudaFree(pl->slot[k].d_order);
     }
     if (pl->ev0) cudaEventDestroy(pl->ev0);
     if (pl->ev1) cudaEventDestroy(pl->ev1);
@@ -452,10 +509,13 @@ static int plan_host_impl(EmpPlanner *pl, const double *scenes, int batch, const
     if (!in_pinned) { memcpy(pl->h_scenes, scenes, sb); h_in = pl->h_scenes; }
     EMP_CK(cudaMemcpyAsync(pl->d_scenes, h_in, sb, cudaMemcpyHostToDevice, pl->stream), "H2D scenes");
     EMP_CK(cudaEventRecord(pl->ev0, pl->stream), "event");
-    int rc = emp_sl_dp_dev(pl->d_scenes, pl->kmax, batch, dp, pl->n_enr_max, pl->d_plans, rows ? pl->d_rows : nullptr, pl->stream);
+    int rc = emp_sl_order_dev(pl->d_scenes, pl->kmax, batch, pl->d_order, pl->stream);
+    if (rc) return rc;
+    rc = emp_sl_dp_dev(pl->d_scenes, pl->kmax, batch, dp, pl->n_enr_max, pl->d_plans, rows ? pl->d_rows : nullptr, pl->d_order,
+                       pl->stream);
     if (rc) return rc;
     if (qp) {
-        rc = emp_sl_qp_dev(pl->d_scenes, pl->kmax, batch, qp, pl->n_enr_max, pl->d_plans, nullptr, pl->stream);
+        rc = emp_sl_qp_dev(pl->d_scenes, pl->kmax, batch, qp, pl->n_enr_max, pl->d_plans, nullptr, pl->d_order, pl->stream);
         if (rc) return rc;
     }
     EMP_CK(cudaEventRecord(pl->ev1, pl->stream), "event");
@@ -482,22 +542,27 @@ int emp_sl_plan_submit(EmpPlanner *pl, int slot, const double *scenes, int batch
     EMP_CK(cudaSetDevice(pl->device), "cudaSetDevice");
     const size_t sb_max = (size_t)pl->max_batch * emp_scene_stride(pl->kmax) * 8;
     const size_t pb_max = (size_t)pl->max_batch * emp_plan_stride(pl->n_enr_max) * 8;
-    if (!S.stream) {
-        EMP_CK(cudaStreamCreateWithFlags(&S.stream, cudaStreamNonBlocking), "slot stream");
-        if (slot == 0) {
-            S.d_scenes = pl->d_scenes; S.d_plans = pl->d_plans; S.d_rows = pl->d_rows;
-            EMP_CK(cudaStreamSynchronize(pl->stream), "planner stream");
-        } else {
-            EMP_CK(cudaMalloc(&S.d_scenes, sb_max), "slot scenes");
-            EMP_CK(cudaMalloc(&S.d_plans, pb_max), "slot plans");
-            EMP_CK(cudaMalloc(&S.d_rows, (size_t)pl->max_batch * pl->max_col * 4), "slot rows");
+    if (!S.stream) {                                   // first use of the slot: its buffers, then (only then) its stream
+        cudaError_t e = cudaSuccess;
+        auto ok = [&](cudaError_t r) { if (e == cudaSuccess) e = r; };
+        ok(cudaMalloc(&S.d_scenes, sb_max));
+        ok(cudaMalloc(&S.d_plans, pb_max));
+        ok(cudaMalloc(&S.d_rows, (size_t)pl->max_batch * pl->max_col * 4));
+        ok(cudaMalloc(&S.d_order, (size_t)pl->max_batch * 4));
+        if (e == cudaSuccess) ok(cudaStreamCreateWithFlags(&S.stream, cudaStreamNonBlocking));
+        if (e != cudaSuccess) {
+            cudaFree(S.d_scenes); cudaFree(S.d_plans); cudaFree(S.d_rows); cudaFree(S.d_order);
+            S.d_scenes = S.d_plans = nullptr;
+            S.d_rows = S.d_order = nullptr;
+            S.stream = nullptr;
+            return fail_cuda(e, "slot allocation");
         }
     }
     const size_t sb = (size_t)batch * emp_scene_stride(pl->kmax) * 8;
     const size_t pb = (size_t)batch * emp_plan_stride(pl->n_enr_max) * 8;
     EMP_CK(cudaMemcpyAsync(S.d_scenes, scenes, sb, cudaMemcpyHostToDevice, S.stream), "H2D scenes");
     if (int rc = emp_sl_plan_dev(S.d_scenes, pl->kmax, batch, dp, qp, pl->n_enr_max, S.d_plans, rows ? S.d_rows : nullptr,
-                                 S.stream)) return rc;
+                                 S.d_order, S.stream)) return rc;
     EMP_CK(cudaMemcpyAsync(plans, S.d_plans, pb, cudaMemcpyDeviceToHost, S.stream), "D2H plans");
     if (rows) EMP_CK(cudaMemcpyAsync(rows, S.d_rows, (size_t)batch * dp->col * 4, cudaMemcpyDeviceToHost, S.stream), "D2H rows");
     S.busy = true;
@@ -843,13 +908,15 @@ int emp_misc_host(EmpPlanner *pl, int op, const double *in, int n, int batch, co
     return 0;
 }
 
-int emp_cycle_path_points_dev(const double *plans, int n_enr_max, int batch, int max_points, double *xy,
-                              int32_t *npts, void *stream) {
-    if (batch < 0 || n_enr_max < 2 || max_points < 3) return fail(-2, "bad batch / n_enr_max / max_points");
+int emp_cycle_path_points_dev(const double *plans, int n_enr_max, const double *scenes, int kmax, int batch,
+                              int max_points, double *xy, int32_t *npts, void *stream) {
+    if (batch < 0 || n_enr_max < 2 || max_points < 4) return fail(-2, "bad batch / n_enr_max / max_points");
+    if (kmax < 0 || kmax > EMP_MAX_KMAX || (kmax & 1)) return fail(-2, "kmax must be even and in [0, 32]");
     if (batch == 0) return 0;
-    if (!plans || !xy || !npts) return fail(-1, "NULL argument");
-    cudaError_t e = emp::launch_cycle_path_points(plans, emp_plan_stride(n_enr_max), n_enr_max, batch, max_points, xy,
-                                                  npts, (cudaStream_t)stream);
+    if (!plans || !scenes || !xy || !npts) return fail(-1, "NULL argument");
+    cudaError_t e = emp::launch_cycle_path_points(plans, emp_plan_stride(n_enr_max), n_enr_max, scenes,
+                                                  emp_scene_stride(kmax), batch, max_points, xy, npts,
+                                                  (cudaStream_t)stream);
     return e == cudaSuccess ? 0 : fail_cuda(e, "cycle_path_points launch");
 }
 
@@ -870,8 +937,9 @@ int emp_st_convex_space_dev(const double *st_out, const double *scenes, int kmax
     if (batch < 0 || n_path < 1) return fail(-2, "bad batch / n_path");
     if (batch == 0) return 0;
     if (!st_out || !scenes || !path || !bounds || !status) return fail(-1, "NULL argument");
-    cudaError_t e = emp::launch_convex_space(st_out, scenes, kmax, path, n_path, p->max_lateral_accel, batch, bounds,
-                                             status, (cudaStream_t)stream);
+    cudaError_t e = emp::launch_convex_space(st_out, scenes, kmax, path, n_path, p->max_lateral_accel,
+                                             p->repair_full_profile == 1 ? 1 : 0, batch, bounds, status,
+                                             (cudaStream_t)stream);
     return e == cudaSuccess ? 0 : fail_cuda(e, "convex_space launch");
 }
 

@@ -4,7 +4,8 @@
 //   test_10.py:234-244  unpacking the Cartesian path into trajectory_x/y/heading/kappa_init + trajectory_index2s
 // cycle_path_points_kernel turns a plan record into the polyline handed to smooth_reference_line (QP#3); the
 // batched cycle has no per-scene reference line among its inputs (BASELINE.json configs[4]), so it plans along the
-// s-axis, for which the projection of frenet_2_x_y_theta_kappa is the identity (x = s, y = l).
+// s-axis, for which the projection of frenet_2_x_y_theta_kappa is the identity (x = s, y = l); like that function
+// (path_planning.py:31-34) it puts the plan-start point in front of the path.
 // cycle_path_tables_kernel lays the smoothed path out as the tables the S-T back half reads.
 #include "emp_common.cuh"
 #include "cycle_kernels.h"
@@ -14,7 +15,8 @@ namespace {
 
 constexpr int PLAN_HDR = 8;
 
-__global__ void cycle_path_points_kernel(const double *__restrict__ plans, int plan_stride, int n_enr_max, int batch,
+__global__ void cycle_path_points_kernel(const double *__restrict__ plans, int plan_stride, int n_enr_max,
+                                         const double *__restrict__ scenes, int scene_stride, int batch,
                                          int max_points, double *__restrict__ xy, int32_t *__restrict__ npts) {
     const int lane = threadIdx.x & 31;
     const int f = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -25,14 +27,19 @@ __global__ void cycle_path_points_kernel(const double *__restrict__ plans, int p
     const bool ok = (int)rec[3] == EMP_QP_OK || (int)rec[3] == EMP_QP_UNKNOWN_MAXITER || (int)rec[3] == EMP_QP_UNKNOWN_NUMERIC || (int)rec[3] == EMP_QP_UNKNOWN_DIVERGED;
     const double *es = rec + PLAN_HDR, *ql = rec + PLAN_HDR + 2 * NE;
     double *o = xy + (size_t)f * max_points * 2;
-    const int m = (ok && n >= 2 && n + 1 <= max_points && n <= NQ) ? n + 1 : 0;
-    for (int i = lane; i < m; i += 32) {
+    // frenet_2_x_y_theta_kappa (path_planning.py:31-34) puts the plan-start point (plan_start_s, plan_start_l) in front of
+    // the n + 1 mid-point path points, so smooth_reference_line sees n + 2 points
+    const double *sc = scenes + (size_t)f * scene_stride;
+    const int m = (ok && n >= 2 && n + 2 <= max_points && n <= NQ) ? n + 2 : 0;
+    for (int j = lane; j < m; j += 32) {
+        const int i = j - 1;
         double s, l;
-        if (i == 0) { s = es[0]; l = ql[0]; }
+        if (j == 0) { s = sc[0]; l = sc[1]; }
+        else if (i == 0) { s = es[0]; l = ql[0]; }
         else if (i == n) { s = es[2 * (n - 1)]; l = ql[n - 1]; }
         else { s = (es[2 * i] + es[2 * (i - 1)]) / 2; l = (ql[i] + ql[i - 1]) / 2; }
-        o[2 * i] = s;
-        o[2 * i + 1] = l;
+        o[2 * j] = s;
+        o[2 * j + 1] = l;
     }
     if (lane == 0) npts[f] = m;
 }
@@ -66,9 +73,11 @@ __global__ void cycle_path_tables_kernel(const double *__restrict__ cart, const 
 
 }  // namespace
 
-cudaError_t launch_cycle_path_points(const double *plans, int plan_stride, int n_enr_max, int batch, int max_points,
-                                     double *xy, int32_t *npts, cudaStream_t st) {
-    cycle_path_points_kernel<<<(batch + 3) / 4, 128, 0, st>>>(plans, plan_stride, n_enr_max, batch, max_points, xy, npts);
+cudaError_t launch_cycle_path_points(const double *plans, int plan_stride, int n_enr_max, const double *scenes,
+                                     int scene_stride, int batch, int max_points, double *xy, int32_t *npts,
+                                     cudaStream_t st) {
+    cycle_path_points_kernel<<<(batch + 3) / 4, 128, 0, st>>>(plans, plan_stride, n_enr_max, scenes, scene_stride, batch,
+                                                              max_points, xy, npts);
     return cudaGetLastError();
 }
 

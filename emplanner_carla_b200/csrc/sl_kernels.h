@@ -25,6 +25,7 @@ struct DpLaunch {
     int off_slab, off_f0, off_nl, off_refc, off_ltab, off_warp, warp_bytes;
     int w_off_cand, w_off_cost, w_off_rows, w_off_offs, w_off_parent, w_off_sj, w_off_dlon, w_off_k0, w_off_wl;
     unsigned smem_bytes;
+    const int32_t *order;     // optional [batch]: work slot -> frame (launch_sl_order); NULL = natural order
 };
 
 enum { QP_MODE_FUSED = 0,      // path from the plan record ([::2]), corridor + QP
@@ -36,10 +37,27 @@ struct QpLaunch {
     int batch, kmax, scene_stride, plan_stride, n_enr_max;
     int n_direct;             // stations per frame in the DIRECT / CORRIDOR modes
     int mode;                 // QP_MODE_*
+    const int32_t *order;     // optional [batch]: ticket -> frame, heaviest frames first (launch_sl_order)
     int n_peers;              // fused all-gather: number of peer slices to push each plan record to
     double *peer[EMP_MAX_PEERS];
+    // arrival flags of the fused all-gather: when the last plan record of the launch has been stored, `epoch` is
+    // written (release, system scope) to this rank's word in every peer's flag array and in its own (0 = no flags)
+    unsigned long long epoch;
+    unsigned long long *self_ready;
+    unsigned long long *peer_ready[EMP_MAX_PEERS];
 };
 
+// Consumer side of the fused all-gather (csrc/sl_qp.cu): spin (acquire, system scope) until flags[r] >= epoch for all
+// r < n_wait, then write `epoch` to every signal[r] (release, system scope).  *err is set to 1 after ~timeout_ms.
+cudaError_t launch_flag_wait_signal(const unsigned long long *flags, int n_wait, unsigned long long epoch,
+                                    unsigned long long *const *signal, int n_signal, int *err, int timeout_ms,
+                                    cudaStream_t st);
+
+// order[0..batch) = frame indices sorted by obstacle count, descending (counting sort, one CTA).  Both kernels' cost
+// grows with the obstacle count (DP: exact evaluations per column; QP: tighter corridors, more iterations), and the
+// slowest frame alone takes ~2/3 of a whole 4096-frame launch: starting the heavy frames first and together is worth
+// 15 % (DP) and 10 % (QP) of the launch (profiles/r2_sched_probe.txt).
+cudaError_t launch_sl_order(const double *scenes, int scene_stride, int kmax, int batch, int32_t *order, cudaStream_t st);
 cudaError_t launch_sl_dp(const double *scenes, double *plans, int32_t *rows, const DpLaunch &p, cudaStream_t st);
 cudaError_t launch_sl_qp(const double *scenes, double *plans, double *lmin_lmax, const double *lmin_in,
                          const double *lmax_in, const double *start_in, double *out_x, int32_t *status_iters,

@@ -18,6 +18,8 @@
 //     with warp shuffles (forward/backward substitution likewise).
 // s, z are carried unscaled (mathematically identical to cvxopt's Nesterov-Todd
 // scaled iterates for the non-negative orthant).
+#include <atomic>
+#include <cstdlib>
 #include "emp_common.cuh"
 #include "sl_kernels.h"
 
@@ -25,7 +27,24 @@ namespace emp {
 
 namespace {
 
+struct FlagPtrs { unsigned long long *p[EMP_MAX_PEERS + 1]; };
+
+__device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ long long globaltimer_ns() {
+    long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+
 constexpr int NR = 14;          // inequality rows per station: 8 vehicle-corner rows + 3 ub + 3 lb
+constexpr int QP_SMEM_ROWS = 4 * NR + 3;   // per warp: 1/s, 1/z, rz, ds o dz per row, and the previous iterate
 #define EMP_UNROLL _Pragma("unroll")
 
 struct Geo {                    // per-launch constants of the dynamics / constraint geometry
@@ -115,14 +134,13 @@ struct Factor {                 // per-lane pieces of the KKT factorisation
 #define EMP_QP_MINBLOCKS 2
 #endif
 
-__global__ void __launch_bounds__(QP_WARPS * 32, EMP_QP_MINBLOCKS)
-sl_qp_kernel(const double *__restrict__ scenes, double *__restrict__ plans, double *__restrict__ lmin_lmax,
-             const double *__restrict__ lmin_in, const double *__restrict__ lmax_in,
-             const double *__restrict__ start_in, double *__restrict__ out_x,
-             int32_t *__restrict__ status_iters, const QpLaunch p) {
-    const int lane = threadIdx.x & 31;
-    const int frame = blockIdx.x * QP_WARPS + (threadIdx.x >> 5);
-    if (frame >= p.batch) return;
+// One frame, one warp.  Everything below is warp-local (registers, shuffles, this warp's slice of shared memory),
+// so the warps of a CTA are independent workers.
+__device__ __forceinline__ void
+qp_one_frame(const int frame, const int lane, const double *__restrict__ scenes, double *__restrict__ plans,
+             double *__restrict__ lmin_lmax, const double *__restrict__ lmin_in, const double *__restrict__ lmax_in,
+             const double *__restrict__ start_in, double *__restrict__ out_x, int32_t *__restrict__ status_iters,
+             const QpLaunch &p) {
     const EmpQpParams &Q = p.q;
 
     // ---------------- inputs ---------------------------------------------------
@@ -482,8 +500,9 @@ EMP_LEVEL_UNROLL
         // Per-row state: s, z live in registers; 1/s, 1/z, rz and the predictor's ds o dz live in shared
         // memory ([row][lane], conflict-free); everything else per row is recomputed where it is used.
         extern __shared__ double qp_smem[];
-        double *sm_is = qp_smem + (size_t)(threadIdx.x >> 5) * (4 * NR * 32) + lane;
+        double *sm_is = qp_smem + (size_t)(threadIdx.x >> 5) * (QP_SMEM_ROWS * 32) + lane;
         double *sm_iz = sm_is + NR * 32, *sm_rz = sm_iz + NR * 32, *sm_ws = sm_rz + NR * 32;
+        double *sm_xp = sm_ws + NR * 32;                           // iterate before the last step (divergence exit)
         double s[NR], z[NR], y[2] = {0.0, 0.0};
         double rx[3] = {0.0, 0.0, 0.0}, ry[2] = {0.0, 0.0};
         EMP_UNROLL
@@ -534,8 +553,13 @@ EMP_LEVEL_UNROLL
                 // Divergence exit (include/emplanner.h, EmpQpParams.diverge_factor): on an infeasible corridor coneqp
                 // has no certificate; cvxopt iterates until its Cholesky breaks down or maxiters and reports 'unknown'.
                 // The gap of a converging solve decreases monotonically, so the first clear increase ends the solve.
-                if (it > 0 && Q.diverge_factor > 0.0 && gap > Q.diverge_factor * gap_min) { qp_status = EMP_QP_UNKNOWN_DIVERGED; break; }
+                if (it > 0 && Q.diverge_factor > 0.0 && gap > Q.diverge_factor * gap_min) {
+                    qp_status = EMP_QP_UNKNOWN_DIVERGED;           // the step that blew the gap up is discarded
+                    x[0] = sm_xp[0]; x[1] = sm_xp[32]; x[2] = sm_xp[64];
+                    break;
+                }
                 gap_min = fmin(gap_min, gap);
+                sm_xp[0] = x[0]; sm_xp[32] = x[1]; sm_xp[64] = x[2];
             }
 
             {
@@ -724,16 +748,124 @@ EMP_LEVEL_UNROLL
     }
 }
 
+// Persistent launch: grid = resident CTAs (EMP_QP_MINBLOCKS per SM), every warp pulls the next frame from a ticket
+// counter until the batch is exhausted.  Solve times differ by 2x between frames (6 .. 13 interior-point iterations),
+// and 4096 frames are 3.46 waves of the 1184 resident warps: with a static frame -> warp mapping the launch ends with a
+// fourth wave that is less than half full; with the queue it ends within one solve of the average.
+// ticket[0] = next frame, ticket[1] = warps that have left the loop; the last one to leave re-arms both for the next
+// launch that is handed this slot (launch_sl_qp rotates slots, so concurrent launches never share one).
+__global__ void __launch_bounds__(QP_WARPS * 32, EMP_QP_MINBLOCKS)
+sl_qp_kernel(const double *__restrict__ scenes, double *__restrict__ plans, double *__restrict__ lmin_lmax,
+             const double *__restrict__ lmin_in, const double *__restrict__ lmax_in,
+             const double *__restrict__ start_in, double *__restrict__ out_x,
+             int32_t *__restrict__ status_iters, unsigned *__restrict__ ticket, const QpLaunch p) {
+    const int lane = threadIdx.x & 31;
+#pragma unroll 1
+    for (;;) {
+        int frame = blockIdx.x * QP_WARPS + (threadIdx.x >> 5);    // static mapping when no queue is given
+        if (ticket != nullptr) {
+            unsigned t = 0;
+            if (lane == 0) t = atomicAdd(ticket, 1u);
+            frame = (int)__shfl_sync(EMP_FULL_MASK, t, 0);
+        }
+        if (frame >= p.batch) break;
+        if (p.order != nullptr) frame = p.order[frame];           // heaviest frames first
+        qp_one_frame(frame, lane, scenes, plans, lmin_lmax, lmin_in, lmax_in, start_in, out_x, status_iters, p);
+        if (ticket == nullptr) return;
+        __syncwarp();
+    }
+    if (ticket == nullptr) return;
+    if (lane == 0) {
+        const unsigned total = gridDim.x * QP_WARPS;
+        if (p.epoch != 0ull) __threadfence_system();             // this warp's peer stores before its arrival below
+        if (atomicAdd(ticket + 1, 1u) == total - 1) {             // every other warp is past its last ticket read
+            ticket[0] = 0u;
+            ticket[1] = 0u;
+            if (p.epoch != 0ull) {
+                // Last warp of the launch: every plan record has been stored (here and in the peers' buffers) and
+                // fenced at system scope before its warp arrived, so publishing the epoch after one more fence makes
+                // the whole shard visible to whoever acquires the flag - no collective, no host round trip.
+                __threadfence_system();
+                for (int r = 0; r < p.n_peers; ++r) st_release_sys(p.peer_ready[r], p.epoch);
+                st_release_sys(p.self_ready, p.epoch);
+            }
+        }
+    }
+}
+
+// Consumer / flow control of the fused all-gather: one thread per flag spins until it reaches `epoch`, then thread 0
+// publishes `epoch` to the words in `signal` (the credit that lets the producers overwrite the buffer again).
+__global__ void flag_wait_signal_kernel(const unsigned long long *flags, int n_wait, unsigned long long epoch,
+                                        FlagPtrs sig, int n_signal, int *err, long long timeout_ns) {
+    __shared__ int bad;
+    if (threadIdx.x == 0) bad = 0;
+    __syncthreads();
+    if ((int)threadIdx.x < n_wait) {
+        const long long t0 = globaltimer_ns();
+        if (err && *reinterpret_cast<volatile int *>(err)) bad = 1;          // an earlier wait already gave up: do not wait again
+        while (!bad && ld_acquire_sys(flags + threadIdx.x) < epoch) {
+            __nanosleep(64);
+            if (globaltimer_ns() - t0 > timeout_ns) {            // never hang the GPU on a lost peer
+                bad = 1;
+                break;
+            }
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        if (bad) {
+            if (err) *err = 1;
+        } else {
+            __threadfence_system();
+            for (int r = 0; r < n_signal; ++r) st_release_sys(sig.p[r], epoch);
+        }
+    }
+}
+
+// Ticket slots (zero-initialised, self re-arming).  One array per device (a __device__ variable is per device).
+__device__ unsigned g_qp_tickets[2 * 256];
+
 }  // namespace
 
 cudaError_t launch_sl_qp(const double *scenes, double *plans, double *lmin_lmax, const double *lmin_in,
                          const double *lmax_in, const double *start_in, double *out_x, int32_t *status_iters,
                          const QpLaunch &p, cudaStream_t st) {
-    const int grid = (p.batch + QP_WARPS - 1) / QP_WARPS;
-    const size_t smem = (size_t)QP_WARPS * 4 * NR * 32 * sizeof(double);
+    static std::atomic<unsigned> next_slot{0};
+    static unsigned *ticket_base[64] = {nullptr};
+    static int sm_count[64] = {0};
+    static const bool persistent = getenv("EMP_QP_STATIC") == nullptr;       // tuning switch: static frame -> warp mapping
+    const size_t smem = (size_t)QP_WARPS * QP_SMEM_ROWS * 32 * sizeof(double);
     cudaFuncSetAttribute(sl_qp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    const int all = (p.batch + QP_WARPS - 1) / QP_WARPS;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    unsigned *ticket = nullptr;
+    int grid = all;
+    if (persistent && dev >= 0 && dev < 64) {
+        if (ticket_base[dev] == nullptr) {
+            void *sym = nullptr;
+            if (cudaGetSymbolAddress(&sym, g_qp_tickets) != cudaSuccess) return cudaGetLastError();
+            cudaDeviceGetAttribute(&sm_count[dev], cudaDevAttrMultiProcessorCount, dev);
+            ticket_base[dev] = static_cast<unsigned *>(sym);
+        }
+        const int resident = sm_count[dev] * EMP_QP_MINBLOCKS;
+        if (all > resident || p.epoch != 0ull) {                   // more frames than resident warps: queue them
+            grid = all < resident ? all : resident;                // (the arrival flags need the "last warp" count too)
+            ticket = ticket_base[dev] + 2 * (next_slot.fetch_add(1) % 256u);
+        }
+    }
+    if (p.epoch != 0ull && ticket == nullptr) return cudaErrorNotSupported;
     sl_qp_kernel<<<grid, QP_WARPS * 32, smem, st>>>(scenes, plans, lmin_lmax, lmin_in, lmax_in, start_in, out_x,
-                                                 status_iters, p);
+                                                 status_iters, ticket, p);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_flag_wait_signal(const unsigned long long *flags, int n_wait, unsigned long long epoch,
+                                    unsigned long long *const *signal, int n_signal, int *err, int timeout_ms,
+                                    cudaStream_t st) {
+    FlagPtrs sig;
+    for (int r = 0; r <= EMP_MAX_PEERS; ++r) sig.p[r] = r < n_signal ? signal[r] : nullptr;
+    flag_wait_signal_kernel<<<1, 32, 0, st>>>(flags, n_wait, epoch, sig, n_signal, err, (long long)timeout_ms * 1000000ll);
     return cudaGetLastError();
 }
 

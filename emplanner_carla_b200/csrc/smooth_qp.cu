@@ -184,6 +184,7 @@ smooth_kernel(const double *__restrict__ xy_in, const int32_t *__restrict__ npts
             for (int q = 0; q < 2; ++q) { s[c][q][0] = s[c][q][1] = 1.0; z[c][q][0] = z[c][q][1] = 1.0; }
         auto hrow = [&](int c, int q, int b) -> double { return b == 0 ? ref[c][q] + thr[c] : -(ref[c][q] - thr[c]); };
         double gap = 0.0, resx0 = 1.0, resz0 = 1.0, gap_min = 0.0;
+        double vp[2][2] = {{0.0, 0.0}, {0.0, 0.0}};        // iterate before the last step (divergence exit)
         double rx[2][2] = {{0, 0}, {0, 0}}, rz[2][2][2], ws3[2][2][2];
         EMP_UNROLL
         for (int c = 0; c < 2; ++c)
@@ -228,8 +229,13 @@ smooth_kernel(const double *__restrict__ xy_in, const int32_t *__restrict__ npts
                 if (pres <= Q.feastol && dres <= Q.feastol && (gap <= Q.abstol || (have_rel && relgap <= Q.reltol))) break;
                 if (it == Q.maxiters) { status = EMP_QP_UNKNOWN_MAXITER; break; }
                 if (!isfinite((gap + resx) + resz)) { status = EMP_QP_UNKNOWN_NUMERIC; break; }
-                if (it > 0 && Q.diverge_factor > 0.0 && gap > Q.diverge_factor * gap_min) { status = EMP_QP_UNKNOWN_DIVERGED; break; }
+                if (it > 0 && Q.diverge_factor > 0.0 && gap > Q.diverge_factor * gap_min) {
+                    status = EMP_QP_UNKNOWN_DIVERGED;              // the step that blew the gap up is discarded
+                    v[0][0] = vp[0][0]; v[0][1] = vp[0][1]; v[1][0] = vp[1][0]; v[1][1] = vp[1][1];
+                    break;
+                }
                 gap_min = fmin(gap_min, gap);
+                vp[0][0] = v[0][0]; vp[0][1] = v[0][1]; vp[1][0] = v[1][0]; vp[1][1] = v[1][1];
             }
             // factor S = H + diag(z/s summed over a variable's two rows), both coordinates
             Fac2 F[2];

@@ -38,7 +38,7 @@ __device__ __forceinline__ int time_index(const double *dp_t, double t) {
 
 __global__ void __launch_bounds__(128)
 convex_space_kernel(const double *__restrict__ st_out, const double *__restrict__ scenes, int kmax,
-                    const double *__restrict__ path, int n_path, double max_lat, int batch,
+                    const double *__restrict__ path, int n_path, double max_lat, int repair_full, int batch,
                     double *__restrict__ bounds, int32_t *__restrict__ status) {
     __shared__ double tab[4][2][NST + 1];                  // per warp: [0]+dp_t, [0]+dp_s
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -55,7 +55,8 @@ convex_space_kernel(const double *__restrict__ st_out, const double *__restrict_
     __syncwarp();
     const unsigned nanmask = __ballot_sync(EMP_FULL_MASK, lane < NST && isnan(my_s));
     const int n_valid = nanmask ? __ffs(nanmask) - 1 : NST;          // stations before the first NaN
-    const int dp_end = nanmask ? n_valid - 1 : NST;                  // :330-333
+    // :330-333; repair R3 (opt-in): a full profile ends at its last index like every profile with a terminator
+    const int dp_end = nanmask ? n_valid - 1 : (repair_full ? NST - 1 : NST);
     // :323-327 - end of the valid part of path_index2s (zero padded)
     int first_pad = n_path;
     for (int k = 1 + lane; k < n_path; k += 32)
@@ -192,9 +193,10 @@ path_speed_merge_kernel(const double *__restrict__ dense, const double *__restri
 }  // namespace
 
 cudaError_t launch_convex_space(const double *st_out, const double *scenes, int kmax, const double *path, int n_path,
-                                double max_lateral_accel, int batch, double *bounds, int32_t *status, cudaStream_t st) {
-    convex_space_kernel<<<(batch + 3) / 4, 128, 0, st>>>(st_out, scenes, kmax, path, n_path, max_lateral_accel, batch,
-                                                         bounds, status);
+                                double max_lateral_accel, int repair_full, int batch, double *bounds, int32_t *status,
+                                cudaStream_t st) {
+    convex_space_kernel<<<(batch + 3) / 4, 128, 0, st>>>(st_out, scenes, kmax, path, n_path, max_lateral_accel, repair_full,
+                                                         batch, bounds, status);
     return cudaGetLastError();
 }
 

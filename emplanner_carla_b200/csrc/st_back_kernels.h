@@ -24,7 +24,8 @@ size_t speed_qp_smem_bytes();
 cudaError_t launch_speed_qp(const double *start, const double *st_out, const double *bounds, double *out,
                             int32_t *status_iters, const SpeedQpLaunch &p, cudaStream_t st);
 cudaError_t launch_convex_space(const double *st_out, const double *scenes, int kmax, const double *path, int n_path,
-                                double max_lateral_accel, int batch, double *bounds, int32_t *status, cudaStream_t st);
+                                double max_lateral_accel, int repair_full, int batch, double *bounds, int32_t *status,
+                                cudaStream_t st);
 cudaError_t launch_increase_points(const double *qp, int batch, double *dense, int32_t *status, cudaStream_t st);
 cudaError_t launch_path_speed_merge(const double *dense, const double *current_time, const double *path, int n_path,
                                     int batch, double *traj, int32_t *status, cudaStream_t st);

@@ -77,11 +77,13 @@ speed_qp_kernel(const double *__restrict__ start, const double *__restrict__ st_
 
     // :415-442 - dp_speed_end = (first NaN of dp_speed_s) - 1; without a terminator dp_speed_s[16] raises IndexError
     const unsigned nanmask = __ballot_sync(EMP_FULL_MASK, lane < EMP_ST_COLS && isnan(rec[8 + lane]));
-    const int end = nanmask ? __ffs(nanmask) - 2 : EMP_ST_COLS;
-    if (!nanmask || end < 1) {
+    // (repair R3, opt-in: a full profile ends at its last column, index 15, like every profile with a terminator)
+    const bool full_ok = !nanmask && Q.repair_full_profile == 1;
+    const int end = nanmask ? __ffs(nanmask) - 2 : (full_ok ? EMP_ST_COLS - 1 : EMP_ST_COLS);
+    if ((!nanmask && !full_ok) || end < 1) {
         for (int i = lane; i < 4 * NQP; i += 32) o[i] = NaN;
         if (lane == 0) {
-            status_iters[2 * f] = nanmask ? EMP_ST_BAD_PROFILE : EMP_ST_INDEX_ERROR;
+            status_iters[2 * f] = (nanmask || full_ok) ? EMP_ST_BAD_PROFILE : EMP_ST_INDEX_ERROR;
             status_iters[2 * f + 1] = 0;
         }
         return;
@@ -355,6 +357,7 @@ speed_qp_kernel(const double *__restrict__ start, const double *__restrict__ st_
 
         // ---- interior-point iterations --------------------------------------------------------------
         double rxv[2], rz[5], ws3[5], tq[5], dsv[5], dz[5];
+        double xp[2] = {0.0, 0.0};                                     // iterate before the last step (divergence exit)
         for (it = 0;; ++it) {
             __syncwarp();
             W.y[lane] = lane < ne ? yv : 0.0;
@@ -399,8 +402,16 @@ speed_qp_kernel(const double *__restrict__ start, const double *__restrict__ st_
             if (pres <= Q.feastol && dres <= Q.feastol && (gap <= Q.abstol || (have_rel && relgap <= Q.reltol))) break;
             if (it == Q.maxiters) { status = EMP_QP_UNKNOWN_MAXITER; break; }
             if (!isfinite((gap + resx) + resz)) { status = EMP_QP_UNKNOWN_NUMERIC; break; }
-            if (it > 0 && Q.diverge_factor > 0.0 && gap > Q.diverge_factor * gap_min) { status = EMP_QP_UNKNOWN_DIVERGED; break; }
+            if (it > 0 && Q.diverge_factor > 0.0 && gap > Q.diverge_factor * gap_min) {
+                status = EMP_QP_UNKNOWN_DIVERGED;                      // the step that blew the gap up is discarded
+                EMP_UNROLL
+                for (int t = 0; t < 2; ++t)
+                    if (vo[t]) W.x[lane + 32 * t] = xp[t];
+                break;
+            }
             gap_min = fmin(gap_min, gap);
+            EMP_UNROLL
+            for (int t = 0; t < 2; ++t) xp[t] = vo[t] ? W.x[lane + 32 * t] : 0.0;
 
             double is[5];
             EMP_UNROLL

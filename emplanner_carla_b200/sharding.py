@@ -40,10 +40,21 @@ class _CudaView:
 
 
 class PeerGatherBuffer:
-    """All-gather without a collective: every rank owns a [world, B, stride] buffer allocated by the library
-    (emp_device_alloc), exports it with CUDA IPC and opens the other ranks' buffers.  The QP kernel then stores
-    each finished plan record into all peers' buffers itself (emp_sl_plan_p2p_dev), so the gather overlaps the
-    solves; `fence()` is the only cross-rank synchronisation (a 1-element all-reduce on the compute stream)."""
+    """All-gather without a collective and without a barrier.
+
+    Every rank owns a [world, B, stride] buffer plus 2 x world flag words, allocated by the library
+    (emp_device_alloc), exported with CUDA IPC and opened by the other ranks.  The QP kernel stores each finished plan
+    record into all peers' buffers itself (NVLink P2P stores overlapping the solves still running) and its last warp
+    publishes the launch's epoch to this rank's `ready` word in every buffer (st.release.sys).  Consumers acquire the
+    flags (`consume()`: a 1-CTA kernel spinning on ld.acquire.sys) only when they read, and hand the buffer back to the
+    producers through the `free` words (credits), which `plan_qp()` waits for before it overwrites the peers' memory
+    again.  NCCL / gloo is used once, to exchange the IPC handles.
+
+        ready[p] in rank c's memory: written by producer p   - "my shard of epoch e is complete in your buffer"
+        free[c]  in rank p's memory: written by consumer c   - "I am done with epoch e of my buffer, overwrite it"
+    """
+
+    FLAG_TIMEOUT_MS = 2000
 
     def __init__(self, batch_per_rank, stride, device, group=None):
         import ctypes as C
@@ -53,18 +64,23 @@ class PeerGatherBuffer:
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
         self.B, self.stride = int(batch_per_rank), int(stride)
-        nbytes = self.world * self.B * self.stride * 8
-        self.base = _lib.lib().emp_device_alloc(nbytes)
+        data_bytes = self.world * self.B * self.stride * 8
+        self._flag_off = (data_bytes + 255) // 256 * 256
+        nbytes = self._flag_off + 2 * self.world * 8
+        self.base = _lib.lib().emp_device_alloc(nbytes)                  # zero-filled
         if not self.base:
             raise _lib.EmpError("emp_device_alloc failed: %s" % _lib.lib().emp_last_error().decode())
         self.full = torch.as_tensor(_CudaView(self.base, (self.world, self.B, self.stride)), device=device)
-        self._token = torch.zeros(1, device=device)
+        self.err = torch.zeros(1, dtype=torch.int32, device=device)
+        self.epoch = 0
+        torch.cuda.synchronize(device)
         self.peer_ptrs, self._opened = [], []
+        ready_ptrs, free_ptrs = [], []
         if self.world > 1:
             handle = (C.c_ubyte * 64)()
             _lib.check(_lib.lib().emp_ipc_export(C.c_void_p(self.base), handle))
             handles = [None] * self.world
-            dist.all_gather_object(handles, bytes(handle), group=group)
+            dist.all_gather_object(handles, bytes(handle), group=group)      # also: every buffer is zeroed by now
             slice_bytes = self.rank * self.B * self.stride * 8          # where MY frames go in every buffer
             for r in range(self.world):
                 if r == self.rank:
@@ -74,7 +90,16 @@ class PeerGatherBuffer:
                 _lib.check(_lib.lib().emp_ipc_open(hb, C.byref(p)))
                 self._opened.append(p)
                 self.peer_ptrs.append(p.value + slice_bytes)
-        self.peer_array = (C.c_void_p * max(len(self.peer_ptrs), 1))(*self.peer_ptrs)
+                ready_ptrs.append(p.value + self._flag_off + 8 * self.rank)
+                free_ptrs.append(p.value + self._flag_off + 8 * (self.world + self.rank))
+        n = max(len(self.peer_ptrs), 1)
+        self.peer_array = (C.c_void_p * n)(*self.peer_ptrs)
+        self._ready_array = (C.c_void_p * n)(*ready_ptrs)
+        self._ready_local = self.base + self._flag_off                  # [world] arrival flags of MY buffer
+        self._free_local = self.base + self._flag_off + 8 * self.world  # [world] credits for MY writes
+        self._self_ready = self._ready_local + 8 * self.rank
+        free_ptrs.append(self._free_local + 8 * self.rank)              # my own credit word
+        self._free_array = (C.c_void_p * len(free_ptrs))(*free_ptrs)
 
     @property
     def mine(self):
@@ -84,10 +109,49 @@ class PeerGatherBuffer:
     def n_peers(self):
         return len(self.peer_ptrs)
 
-    def fence(self):
-        """Stream-ordered barrier: when it completes every rank's kernels (and their peer stores) have finished."""
-        if self.world > 1:
-            dist.all_reduce(self._token, group=self.group)
+    def _stream(self):
+        return self._C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+    def plan_qp(self, scenes, qp, n_enr_max, order=None):
+        """The corridor + QP launch of one planning step on torch's current stream, writing this rank's shard into
+        every rank's buffer and publishing a new epoch.  (The DP launch that precedes it only writes `mine`.)"""
+        L, C = self._lib.lib(), self._C
+        self.epoch += 1
+        if self.epoch > 1:                                              # credits: everybody consumed the previous epoch
+            self._lib.check(L.emp_gather_wait_signal_dev(C.c_void_p(self._free_local), self.world, self.epoch - 1, None,
+                                                         0, C.c_void_p(self.err.data_ptr()), self.FLAG_TIMEOUT_MS,
+                                                         self._stream()))
+        kmax = (scenes.shape[1] - 6) // 2
+        self._lib.check(L.emp_sl_qp_gather_dev(C.c_void_p(scenes.data_ptr()), kmax, scenes.shape[0], C.byref(qp),
+                                               int(n_enr_max), C.c_void_p(self.mine.data_ptr()), self.n_peers,
+                                               self.peer_array, self.epoch, C.c_void_p(self._self_ready),
+                                               self._ready_array, C.c_void_p(order.data_ptr()) if order is not None else None,
+                                               self._stream()))
+
+    def consume(self):
+        """Enqueue the consumer side on torch's current stream: wait until every rank's shard of the current epoch
+        has arrived in this buffer, then give the buffer back to all producers.  Work enqueued after this call on the
+        same stream may read `gathered()`; it must be enqueued BEFORE the call if it has to finish before the
+        buffer is overwritten - use `wait_arrival()` + `release()` around it in that case."""
+        L, C = self._lib.lib(), self._C
+        self._lib.check(L.emp_gather_wait_signal_dev(C.c_void_p(self._ready_local), self.world, self.epoch,
+                                                     self._free_array, len(self._free_array),
+                                                     C.c_void_p(self.err.data_ptr()), self.FLAG_TIMEOUT_MS, self._stream()))
+
+    def wait_arrival(self):
+        L, C = self._lib.lib(), self._C
+        self._lib.check(L.emp_gather_wait_signal_dev(C.c_void_p(self._ready_local), self.world, self.epoch, None, 0,
+                                                     C.c_void_p(self.err.data_ptr()), self.FLAG_TIMEOUT_MS, self._stream()))
+
+    def release(self):
+        L, C = self._lib.lib(), self._C
+        self._lib.check(L.emp_gather_wait_signal_dev(None, 0, self.epoch, self._free_array, len(self._free_array),
+                                                     C.c_void_p(self.err.data_ptr()), self.FLAG_TIMEOUT_MS, self._stream()))
+
+    def check(self):
+        """Host-side check after a synchronize: no flag wait timed out."""
+        if int(self.err.item()) != 0:
+            raise self._lib.EmpError("a gather flag wait timed out (a peer rank never delivered its shard)")
 
     def gathered(self):
         return self.full.view(self.world * self.B, self.stride)

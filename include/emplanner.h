@@ -114,8 +114,12 @@ typedef struct EmpSpeedQpParams {     /* speed_QP :403-404, generate_convex_spac
     double max_lateral_accel;         /* 0.2 * 9.8 */
     double abstol, reltol, feastol;   /* 1e-7, 1e-6, 1e-7 */
     int32_t maxiters;                 /* 100 */
-    int32_t reserved;
-    double diverge_factor;            /* 2, as in EmpQpParams */
+    int32_t repair_full_profile;      /* 0.  1 = repair R3: a DP speed profile that fills all 16 columns (no NaN
+                                         terminator) ends at index 15 instead of raising the reference's IndexError at
+                                         dp_speed_s[16] (speed_planning_test.py:415-428: `dp_speed_end = 16` is the
+                                         MATLAB original's 1-based count, every other branch sets the 0-based index) */
+    double diverge_factor;            /* 100: same rule as EmpQpParams, looser - the gap of a converging speed QP is not
+                                         monotone in its first iterations (ratios up to 11 on the golden frames) */
 } EmpSpeedQpParams;
 
 void emp_speed_qp_params_default(EmpSpeedQpParams *p);
@@ -159,9 +163,16 @@ typedef struct EmpPlanner EmpPlanner;   /* host-buffer planner handle, see below
  * planning_utils.cal_quintic_coefficient (:671).
  * scenes: [batch, emp_scene_stride(kmax)]; plans: [batch, emp_plan_stride(n_enr_max)]
  * (words 0,2,5 and the enriched arrays are written); rows: optional [batch, col]
- * int32 lattice row per column (-1 for K == 0 frames), may be NULL. */
+ * int32 lattice row per column (-1 for K == 0 frames), may be NULL.
+ * order: optional [batch] schedule from emp_sl_order_dev (work slot -> frame); NULL = frames in their own order.
+ * The schedule only decides which warp works on which frame; every result is written at the frame's own index. */
 int emp_sl_dp_dev(const double *scenes, int kmax, int batch, const EmpDpParams *p,
-                  int n_enr_max, double *plans, int32_t *rows, void *stream);
+                  int n_enr_max, double *plans, int32_t *rows, const int32_t *order, void *stream);
+
+/* Schedule for the two kernels: order[0..batch) = frame indices by obstacle count, descending (one small launch).
+ * Both kernels' cost grows with the obstacle count and one heavy frame alone takes ~2/3 of the time of a 4096-frame
+ * launch, so the heavy frames are started first (DP) / handed out first by the ticket queue (QP). */
+int emp_sl_order_dev(const double *scenes, int kmax, int batch, int32_t *order, void *stream);
 
 /* Corridor + QP smoother for a batch, one launch; reads the enriched path that
  * emp_sl_dp_dev left in `plans`, takes every 2nd point (test_9.py:187-188).
@@ -170,7 +181,7 @@ int emp_sl_dp_dev(const double *scenes, int kmax, int batch, const EmpDpParams *
  * the qp arrays of each plan record.  lmin_lmax: optional [batch, 2, NQ] copy of
  * the corridor, may be NULL. */
 int emp_sl_qp_dev(const double *scenes, int kmax, int batch, const EmpQpParams *p,
-                  int n_enr_max, double *plans, double *lmin_lmax, void *stream);
+                  int n_enr_max, double *plans, double *lmin_lmax, const int32_t *order, void *stream);
 
 /* Quadratic_planning alone on caller-supplied corridors (l_min/l_max: [batch, n]). */
 int emp_qp_dev(const double *l_min, const double *l_max, const double *start_l_dl_ddl /*[batch,3]*/,
@@ -182,9 +193,11 @@ int emp_qp_dev(const double *l_min, const double *l_max, const double *start_l_d
 int emp_corridor_dev(const double *dp_s, const double *dp_l, int n, const double *scenes, int kmax, int batch,
                      const EmpQpParams *p, double *lmin_lmax, int32_t *status_iters, void *stream);
 
-/* DP -> [::2] -> corridor -> QP: the S-L planning step (two launches on `stream`). */
+/* DP -> [::2] -> corridor -> QP: the S-L planning step (two launches on `stream`; three with order_ws != NULL:
+ * a [batch] int32 workspace that receives the emp_sl_order_dev schedule both kernels then follow). */
 int emp_sl_plan_dev(const double *scenes, int kmax, int batch, const EmpDpParams *dp,
-                    const EmpQpParams *qp, int n_enr_max, double *plans, int32_t *rows, void *stream);
+                    const EmpQpParams *qp, int n_enr_max, double *plans, int32_t *rows, int32_t *order_ws,
+                    void *stream);
 
 /* ---- Cartesian <-> Frenet (K4) ---------------------------------------------------------
  * lines: [batch, n_nodes, 4] reference line per scene as (x, y, theta, kappa) rows - the output of
@@ -286,13 +299,14 @@ int emp_st_back_host(EmpPlanner *pl, int batch, const EmpSpeedQpParams *p,
 /* ---- glue between the S-L and the S-T half of an EM cycle (K10) ---------------------------------
  * In the reference this is list handling inside the driver scripts, not planner functions.
  * emp_cycle_path_points_dev: test_9.py:204-210 - mid-point averaging of (dp_path_s[::2], qp_path_l) of every plan
- *   record into the polyline handed to smooth_reference_line (QP#3), planned along the s-axis (x = s, y = l).
- *   xy [batch, max_points, 2]; npts [batch] = n_qp + 1, or 0 when the frame has no QP path.
+ *   record, behind the plan-start point of the frame's scene record (path_planning.py:31-34), into the polyline handed
+ *   to smooth_reference_line (QP#3), planned along the s-axis (x = s, y = l).
+ *   xy [batch, max_points, 2]; npts [batch] = n_qp + 2, or 0 when the frame has no QP path.
  * emp_cycle_path_tables_dev: test_10.py:234-244 - (x, y, theta, kappa) rows cart [batch, max_points, 4] (output
  *   of emp_smooth_line_dev) -> path2 [batch,2,n_path] = (trajectory_index2s, kappa) zero padded, and
  *   path5 [batch,5,n_path] = (path_s, x, y, heading, kappa) NaN padded; n_path > max(npts). */
-int emp_cycle_path_points_dev(const double *plans, int n_enr_max, int batch, int max_points, double *xy,
-                              int32_t *npts, void *stream);
+int emp_cycle_path_points_dev(const double *plans, int n_enr_max, const double *scenes, int kmax, int batch,
+                              int max_points, double *xy, int32_t *npts, void *stream);
 int emp_cycle_path_tables_dev(const double *cart, const int32_t *npts, int max_points, int batch, int n_path,
                               double *path2, double *path5, void *stream);
 
@@ -351,11 +365,28 @@ int emp_misc_host(EmpPlanner *pl, int op, const double *in, int n, int batch, co
  * "single NCCL all-gather of the solved paths" with P2P writes from inside the QP kernel. */
 int emp_sl_plan_p2p_dev(const double *scenes, int kmax, int batch, const EmpDpParams *dp, const EmpQpParams *qp,
                         int n_enr_max, double *plans, int32_t *rows, int n_peers, double *const *peer_slices,
-                        void *stream);
+                        int32_t *order_ws, void *stream);
 
 /* The corridor+QP launch of the fused step alone (for callers that time the two kernels separately). */
 int emp_sl_qp_p2p_dev(const double *scenes, int kmax, int batch, const EmpQpParams *qp, int n_enr_max,
-                      double *plans, int n_peers, double *const *peer_slices, void *stream);
+                      double *plans, int n_peers, double *const *peer_slices, const int32_t *order, void *stream);
+
+/* The same launch with arrival flags instead of a cross-rank barrier: when the last plan record of the launch has been
+ * stored (locally and into every peer slice), `epoch` (> 0, increasing per use of the buffer) is written with release
+ * semantics at system scope to *self_ready and to every *peer_ready[r] - this rank's word in the flag array of its own
+ * and of each peer's gather buffer.  A consumer that acquires flag >= epoch sees the whole shard.
+ * emp_gather_wait_signal_dev is that consumer and the flow control in one tiny launch: it spins (ld.acquire.sys) until
+ * flags[r] >= epoch for all r < n_wait, then writes `epoch` (st.release.sys) to every signal[r], r < n_signal - e.g.
+ * wait for all shards of a gather buffer, then tell every producer that the buffer may be overwritten (credit).  With
+ * n_signal = 0 it only waits; with n_wait = 0 it only signals.  After timeout_ms (<= 0: 2000) without progress *err is
+ * set to 1 and nothing is signalled (the GPU is never left spinning on a lost peer).
+ * Together they replace the north_star's NCCL all-gather AND its completion barrier with NVLink stores from inside
+ * the QP kernel; NCCL (torch.distributed) is only used to exchange the IPC handles at start-up. */
+int emp_sl_qp_gather_dev(const double *scenes, int kmax, int batch, const EmpQpParams *qp, int n_enr_max,
+                         double *plans, int n_peers, double *const *peer_slices, uint64_t epoch,
+                         uint64_t *self_ready, uint64_t *const *peer_ready, const int32_t *order, void *stream);
+int emp_gather_wait_signal_dev(const uint64_t *flags, int n_wait, uint64_t epoch, uint64_t *const *signal,
+                               int n_signal, int32_t *err, int timeout_ms, void *stream);
 
 /* Device buffers that can be shared between the per-GPU processes of one box (CUDA IPC). */
 void *emp_device_alloc(size_t bytes);
@@ -393,7 +424,9 @@ int emp_qp_host(EmpPlanner *pl, const double *l_min, const double *l_max, const 
 int emp_corridor_host(EmpPlanner *pl, const double *dp_s, const double *dp_l, int n, const double *scenes,
                       int batch, const EmpQpParams *p, double *lmin_lmax, int32_t *status_iters);
 /* Page-locked host buffers.  The *_host entry points DMA straight from/to buffers that are page-locked
- * (these, cudaHostRegister'ed, or torch pinned memory) and stage pageable ones through internal pinned buffers. */
+ * (these, cudaHostRegister'ed, or torch pinned memory) and stage pageable ones through internal pinned buffers.
+ * The synchronous *_host entry points run on the planner's own stream and device buffers; every submit slot has its
+ * own stream and buffers, so synchronous calls and in-flight slots never share memory. */
 void *emp_host_alloc(size_t bytes);
 void emp_host_free(void *p);
 /* Kernel-only time (ms, CUDA events on the planner's stream) of the last *_host call. */

@@ -66,8 +66,8 @@ def qp(P, q, G, h, A=None, b=None, maxiters=MAXITERS, abstol=ABSTOL, reltol=RELT
 
     diverge_factor (None/0 = cvxopt behaviour): documented early exit of the GPU kernels
     (EmpQpParams.diverge_factor, csrc/sl_qp.cu): a duality gap above diverge_factor x the
-    smallest gap of the earlier iterations ends the solve with status 'unknown' and the current
-    iterate.  coneqp has no infeasibility certificate: on an infeasible problem cvxopt goes on for
+    smallest gap of the earlier iterations ends the solve with status 'unknown' and the PREVIOUS
+    iterate x (the last one reached before the gap grew; y, s, z are left at the current one).  coneqp has no infeasibility certificate: on an infeasible problem cvxopt goes on for
     a few more iterations until its Cholesky breaks down (status 'unknown' as well), through
     iterates that are no longer a numerically well defined function of the input (two exact-
     arithmetic-equivalent factorisations differ by O(1 m) there, profiles/parity_r2.json); the
@@ -139,8 +139,10 @@ def qp(P, q, G, h, A=None, b=None, maxiters=MAXITERS, abstol=ABSTOL, reltol=RELT
         if not (np.isfinite(gap) and np.isfinite(resx) and np.isfinite(resz)):
             return result("unknown", it)
         if diverge_factor and it > 0 and gap > diverge_factor * gap_min:
+            x = x_prev                                  # the step that blew the gap up is discarded
             return result("unknown", it)
         gap_min = min(gap_min, gap)
+        x_prev = x
 
         if it == 0:
             d = np.sqrt(s / z)                      # misc.compute_scaling

@@ -463,8 +463,12 @@ def make_motion_planning(n_frames=40):
         refshim.diverge_factor = df
         refshim.qp_log_enabled = True
         refshim.qp_log.clear()
-        sent = _quiet(mpc.replay, text, pu, pp, msgs)
+        calls = []
+        sent = _quiet(mpc.replay, text, mpc.RecordingProxy(pu, calls), mpc.RecordingProxy(pp, calls), msgs)
         refshim.diverge_factor = None
+        if tag == "refd":                                     # every planner call of the caller, for the forced replay
+            import json
+            rec["refd_calls_json"] = np.array(json.dumps(calls))
         assert len(sent) == F and len(refshim.qp_log) == 3 * F
         rec[tag + "_cart"] = np.full((F, 28, 4), np.nan)
         rec[tag + "_cart_n"] = np.zeros(F, np.int32)
@@ -485,7 +489,27 @@ def make_motion_planning(n_frames=40):
                 r = refshim.qp_log[3 * f + q]["result"]
                 rec[tag + "_qp_status"][f, q] = int(r["status"] == "optimal")
                 rec[tag + "_qp_iters"][f, q] = r["iterations"]
+    # Q10 sensitivity of the reference itself: the same frames with the ego / plan-start positions moved by 1e-9 m.
+    # `int(end_s - start_s)` (path_planning.py:405) turns the last bits of plan_start_s into a path that is one point
+    # longer or shorter, so the reference does not reproduce its own output length under input noise of that size.
+    moved = []
+    for m in msgs:
+        m = list(m)
+        m[2] = (m[2][0] + 1e-9, m[2][1] - 1e-9)
+        m[3] = (m[3][0] + 1e-9, m[3][1] - 1e-9)
+        moved.append(tuple(m))
+    refshim.diverge_factor = DIVERGE_FACTOR
+    sent = _quiet(mpc.replay, text, pu, pp, moved)
+    refshim.diverge_factor = None
+    rec["refd_moved_path_n"] = np.array([len(p[2]) for p in sent], np.int32)
+    rec["refd_moved_path_l"] = np.full((F, 27), np.nan)
+    rec["refd_moved_path_s"] = np.full((F, 27), np.nan)
+    for f, p in enumerate(sent):
+        rec["refd_moved_path_s"][f, :len(p[2])] = p[2]
+        rec["refd_moved_path_l"][f, :len(p[3])] = np.array(p[3], dtype=np.float64).reshape(-1)
     np.savez_compressed(os.path.join(GOLDEN, "motion_planning.npz"), ref_commit=REF_COMMIT, **rec)
+    print("reference vs itself with inputs moved by 1e-9 m: path length differs on %d of %d frames"
+          % (int((rec["refd_moved_path_n"] != rec["refd_path_n"]).sum()), F))
     unk = (rec["ref_qp_status"][:, 1] == 0)
     same = [f for f in range(F) if np.array_equal(rec["ref_cart"][f], rec["refd_cart"][f], equal_nan=True)]
     print("motion_planning done: %d frames, path QP 'unknown' on %d, payload identical with/without the divergence exit on %d"

@@ -19,6 +19,12 @@ oracle/make_golden.py).  The solve itself follows the documented repair
       infinite bounds are dropped - the MATLAB call this draft was ported from, quadprog(H,f,A,b,Aeq',beq,lb,ub);
       the start pins lb = ub stay an opposing inequality pair, as in Quadratic_planning (path_planning.py:148-166);
 
+  R3  (opt-in, `repair_full_profile`) a DP profile that fills all 16 columns ends at index 15.  The draft sets
+      `dp_speed_end = 16` / `dp_speed_end_index = len(dp_speed_s)` when it finds no NaN (:330,:416) - the 1-based count of
+      the MATLAB original - while the NaN branch sets the 0-based index of the last valid entry (`i - 1`); the count is
+      then used as an index (`dp_speed_s[16]`, :428; `dp_speed_t[16]`, :391) and raises IndexError.  With the default
+      reference_speed = 50 m/s ~75 % of the synthetic profiles are full, so without R3 most frames never reach the QP;
+
 and uses oracle/coneqp.py for the QP (parity unpinned at the cvxopt boundary, see that file).
 Exceptions of the reference that are part of the contract: IndexError when the DP profile has no NaN terminator
 (`dp_speed_s[16]`, :428; `relative_time_init[17]`, :538; `dp_speed_t[16]`, :391), ValueError from scipy's interp1d
@@ -64,13 +70,14 @@ def _time_index(dp_t, t):
     return 0
 
 
-def convex_space(dp_s, dp_t, index2s, s_in, s_out, t_in, t_out, kappa, max_lateral_accel=0.2 * 9.8):
-    """generate_convex_space.  Returns s_lb, s_ub, s_dot_lb, s_dot_ub (16 each)."""
+def convex_space(dp_s, dp_t, index2s, s_in, s_out, t_in, t_out, kappa, max_lateral_accel=0.2 * 9.8,
+                 repair_full_profile=False):
+    """generate_convex_space.  Returns s_lb, s_ub, s_dot_lb, s_dot_ub (16 each).  repair_full_profile: repair R3."""
     n = N_ST
     s_lb, s_ub = np.ones(n) * -np.inf, np.ones(n) * np.inf
     sd_lb, sd_ub = np.ones(n) * -np.inf, np.ones(n) * np.inf
     idx_end = len(index2s)
-    dp_end = len(dp_s)
+    dp_end = len(dp_s) - 1 if repair_full_profile else len(dp_s)
     for k in range(1, len(index2s)):
         if index2s[k] == 0 and index2s[k - 1] != 0:
             idx_end = k - 1
@@ -104,9 +111,10 @@ def convex_space(dp_s, dp_t, index2s, s_in, s_out, t_in, t_out, kappa, max_later
     return s_lb, s_ub, sd_lb, sd_ub
 
 
-def speed_qp_setup(dp_s, dp_t):
-    """:415-442: (dp_speed_end, qp_size, dt)."""
-    end = 16
+def speed_qp_setup(dp_s, dp_t, repair_full_profile=False):
+    """:415-442: (dp_speed_end, qp_size, dt).  repair_full_profile = repair R3 (opt-in): a profile without a NaN
+    terminator ends at its last index (15) instead of the reference's `dp_speed_end = 16` -> IndexError (:428)."""
+    end = 15 if repair_full_profile else 16
     for i in range(len(dp_s)):
         if np.isnan(dp_s[i]):
             end = i - 1
@@ -119,10 +127,10 @@ def speed_qp_setup(dp_s, dp_t):
 
 
 def speed_qp_matrices(v0, a0, dp_s, dp_t, s_lb, s_ub, sd_lb, sd_ub, w_cost_s_dot2=10, w_cost_v_ref=50,
-                      w_cost_jerk=500, reference_speed=50):
+                      w_cost_jerk=500, reference_speed=50, repair_full_profile=False):
     """What speed_QP builds (:434-499) plus the separate lb/ub of repair R2.
     Returns dict(H, f, A, b, Aeq, beq, lb, ub, dt, qp_size); Aeq is 3q x (2q-2) as in the reference."""
-    end, q, dt = speed_qp_setup(dp_s, dp_t)
+    end, q, dt = speed_qp_setup(dp_s, dp_t, repair_full_profile)
     nv = 3 * q
     Aeq = np.zeros((nv, 2 * q - 2))
     beq = np.zeros((2 * q - 2, 1))

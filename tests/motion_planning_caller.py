@@ -152,3 +152,113 @@ def messages_from_golden(g):
         msgs.append((stat, dyn, pt(g["ego"]), pt(g["pred"]), pt(g["vel"]), pt(g["acc"]), route,
                      [int(v) for v in g["first_match"]]))
     return msgs
+
+
+# ---- per-call recording / teacher forcing ---------------------------------------------------------------------
+# The reference pipeline is chaotic at the 1e-9 level: `int(end_s - start_s)` (path_planning.py:405) turns the last
+# bits of plan_start_s into a path that is one point longer or shorter, and near-tie lattice decisions flip, so the
+# unmodified reference does not reproduce its OWN payloads when its inputs move by 1e-9 m (20 of 40 golden frames
+# change length; oracle/make_golden.py::make_motion_planning).  A free-running replay can therefore only agree
+# frame by frame where no such discrete event happens.  The forced replay removes the chaos without touching the
+# caller: the planner modules handed to motion_planning() are proxies that run the drop-in on the caller's arguments,
+# compare its answer with what the reference answered to the same call, and hand the REFERENCE's answer back to the
+# caller - so every call of every frame is checked on exactly the inputs the reference saw, in the reference's own
+# call sequence, argument types and keywords.
+
+PLANNER_CALLS = ("find_match_points", "sampling", "smooth_reference_line", "cal_s_map_fun", "cal_s_l_fun",
+                 "cal_s_l_deri_fun", "DP_algorithm", "cal_lmin_lmax", "Quadratic_planning", "frenet_2_x_y_theta_kappa")
+
+
+def _plain(v):
+    """Nested tuples/lists/ndarrays -> nested lists of python floats/ints (pickle-free, comparable)."""
+    import numpy as np
+    if isinstance(v, (list, tuple)):
+        return [_plain(x) for x in v]
+    if isinstance(v, np.ndarray):
+        return [_plain(x) for x in v.tolist()] if v.ndim else v.item()
+    if isinstance(v, np.generic):
+        return v.item()
+    return v
+
+
+class RecordingProxy:
+    """Wraps a planner module: every call in PLANNER_CALLS is appended to `log` as (name, plain outputs)."""
+
+    def __init__(self, module, log):
+        self._m, self._log = module, log
+
+    def __getattr__(self, name):
+        fn = getattr(self._m, name)
+        if name not in PLANNER_CALLS:
+            return fn
+
+        def call(*a, **k):
+            out = fn(*a, **k)
+            self._log.append((name, _plain(out)))
+            return out
+        return call
+
+
+def _max_abs(a, b):
+    import numpy as np
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    if a.shape != b.shape:
+        return float("inf")
+    return float(np.abs(a - b).max()) if a.size else 0.0
+
+
+class ForcingProxy:
+    """Wraps a drop-in planner module for the forced replay (see above).  `recorded` is the reference's call log
+    (list of (name, outputs)); `report` collects, per call name, the worst deviation of the drop-in's answer."""
+
+    def __init__(self, module, recorded, report, cursor):
+        self._m, self._rec, self._rep, self._cur = module, recorded, report, cursor
+
+    def __getattr__(self, name):
+        fn = getattr(self._m, name)
+        if name not in PLANNER_CALLS:
+            return fn
+
+        def call(*a, **k):
+            import numpy as np
+            i = self._cur[0]
+            self._cur[0] += 1
+            want_name, want = self._rec[i]
+            if want_name != name:
+                raise AssertionError("call %d: the caller invoked %s where the reference invoked %s" % (i, name, want_name))
+            try:
+                got = _plain(fn(*a, **k))
+            except Exception as e:                                    # keep the replay alive, report the failure
+                self._rep.setdefault(name, {"calls": 0, "worst": 0.0, "shape_mismatch": 0, "errors": []})
+                self._rep[name]["errors"].append("%s: %s" % (type(e).__name__, e))
+                got = None
+            r = self._rep.setdefault(name, {"calls": 0, "worst": 0.0, "shape_mismatch": 0, "errors": []})
+            r["calls"] += 1
+            if got is not None:
+                if name == "find_match_points":                      # (index list, projection list)
+                    if got[0] != want[0]:
+                        r["shape_mismatch"] += 1                      # a different match index is a discrete mismatch
+                    r["worst"] = max(r["worst"], _max_abs(got[1], want[1]))
+                elif name in ("smooth_reference_line", "frenet_2_x_y_theta_kappa"):
+                    g_, w_ = np.asarray(got, dtype=np.float64), np.asarray(want, dtype=np.float64)
+                    if g_.shape != w_.shape:
+                        r["shape_mismatch"] += 1
+                    else:                                             # columns x, y | theta | kappa tracked separately
+                        for key, sl in (("xy", slice(0, 2)), ("theta", slice(2, 3)), ("kappa", slice(3, 4))):
+                            r["worst_" + key] = max(r.get("worst_" + key, 0.0), float(np.abs(g_[:, sl] - w_[:, sl]).max()))
+                        r["worst"] = max(r["worst"], r["worst_xy"])
+                else:
+                    d = _max_abs(got, want)
+                    if d == float("inf"):
+                        r["shape_mismatch"] += 1
+                    else:
+                        r["worst"] = max(r["worst"], d)
+            # teacher forcing: the caller continues with the reference's own answer
+            if name in ("cal_lmin_lmax",):
+                return tuple(np.array(x) for x in want)
+            if name in ("find_match_points", "cal_s_l_fun", "cal_s_l_deri_fun", "DP_algorithm", "Quadratic_planning"):
+                return tuple(want)
+            if name in ("sampling", "smooth_reference_line", "frenet_2_x_y_theta_kappa"):
+                return [tuple(x) for x in want]
+            return want
+        return call

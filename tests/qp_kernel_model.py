@@ -180,8 +180,9 @@ def solve_qp(lmin, lmax, st, ds=2.0, w_l=1000, w_ddl=3000, w_dddl=150, w_c=250, 
         if not np.isfinite(gap + resx + resz):
             return x, 'unknown', it
         if diverge_factor and it > 0 and gap > diverge_factor * gap_min:
-            return x, 'unknown', it
+            return x_prev, 'unknown', it
         gap_min = min(gap_min, gap)
+        x_prev = x
         isv = 1.0 / s
         w = z * isv
         F = factor(w)

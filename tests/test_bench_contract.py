@@ -26,18 +26,29 @@ def test_reference_arm_line_on_cpu():
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
     assert d["e2e"] == {"value": d["value"], "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert d["vs_baseline"] is None and d["dtype"] == "f64" and "workload" in d["config"]
+    # the two arms name the same workload (the driver compares config.workload)
+    sys.path.insert(0, ROOT)
+    import bench
+    from emplanner_carla_b200 import scenes
+    assert d["config"]["workload"] == bench.workload_string(4096, scenes.LATTICE_A)
 
 
 @pytest.mark.gpu
 def test_product_arm_line_on_gpu():
-    d = _run(["--steps", "3", "--warmup", "3", "--cpu-frames", "32", "--batch", "512"])
+    d = _run(["--steps", "3", "--warmup", "3", "--cpu-frames", "32", "--batch", "512", "--min-seconds", "0.05"])
     assert BASE_KEYS <= set(d) and "impl" not in d
+    assert d["regions"]["count"] >= 3 and abs(d["ms_per_step"] * d["steps"] - d["regions"]["median_ms"]) < 1e-9
+    assert d["regions"]["timed_total_s"] >= 0.04
+    assert "flush" not in d["config"]["l2"].split(";")[0] and "rotate" in d["config"]["l2"]
+    assert d["extra"]["config2"]["global_batch"] == 8192 and d["extra"]["config2"]["value"] > 0
+    assert d["extra"]["config4"]["bug_compatible"]["value"] > 0
     assert d["n_gpus"] == 1 and d["steps"] == 3 and d["higher_is_better"] is True and d["scaling"] == "weak"
     r = d["roofline"]
     assert r["bound"] == "hbm" and r["unit"] == "GB/s" and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-12
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["value"] > 0 and d["cpu_baseline"]["sample"]
     e = d["e2e"]
     assert e["value"] > 0 and e["h2d_bytes_per_step"] == 512 * 22 * 8 and e["d2h_bytes_per_step"] == 512 * 224 * 8
-    assert d["gpu_launches"] == 6 and d["value"] > d["cpu_baseline"]["value"]
+    assert d["gpu_launches"] == 9 and d["value"] > d["cpu_baseline"]["value"]           # schedule + DP + QP per step
+    assert set(d["kernels_ms"]) == {"sl_order_kernel", "sl_dp_kernel", "sl_qp_kernel", "collective"}
     assert set(d["clocks"]) >= {"sm_mhz", "sm_max_mhz", "reasons"}
     assert d["pipeline"]["batches_in_flight"] >= 1 and d["pipeline"]["value_serial_steps"] > 0

@@ -9,7 +9,7 @@ import pytest
 pytestmark = pytest.mark.gpu
 
 
-def _oracle_frame(sc, f, lat):
+def _oracle_frame(sc, f, lat, r3=False):
     from oracle import sl_dp, sl_qp, frenet, st_misc, st_dp, st_back
     sl, st = sc["sl"], sc["st"]
     K = int(sl["nobs"][f])
@@ -22,10 +22,11 @@ def _oracle_frame(sc, f, lat):
         lmin, lmax = sl_qp.corridor(dp_s, dp_l, obs_s, obs_l, 5, 5)
     except IndexError:
         return r
-    ql, _, _, info = sl_qp.quadratic_planning(lmin, lmax, *start[1:])
+    ql, _, _, info = sl_qp.quadratic_planning(lmin, lmax, *start[1:], diverge_factor=2.0)
     r.update(qp_l=ql, qp_optimal=info["status"] == "optimal")
     ps, pl = sl_qp.midpoint_path(dp_s, ql)
-    line, sinfo = frenet.smooth_reference_line(list(zip(ps, pl)))
+    # frenet_2_x_y_theta_kappa puts the plan-start point in front (path_planning.py:31-34); along the s-axis x = s, y = l
+    line, sinfo = frenet.smooth_reference_line([(start[0], start[1])] + list(zip(ps, pl)), diverge_factor=2.0)
     line = np.array(line)
     r.update(cart=line, smooth_optimal=sinfo["status"] == "optimal")
     nan = [np.nan]
@@ -35,9 +36,10 @@ def _oracle_frame(sc, f, lat):
     r.update(dp_s=dp["dp_s"], dp_t=dp["dp_t"])
     try:
         cs = st_back.convex_space(dp["dp_s"], dp["dp_t"], idx2s, st["s_in"][f], st["s_out"][f], st["t_in"][f],
-                                  st["t_out"][f], np.append(line[:, 3], [0.0]))
+                                  st["t_out"][f], np.append(line[:, 3], [0.0]), repair_full_profile=r3)
         r["bounds"] = np.array(cs)
-        q = st_back.speed_qp(st["v0"][f], sc["a0"][f], dp["dp_s"], dp["dp_t"], *cs)
+        q = st_back.speed_qp(st["v0"][f], sc["a0"][f], dp["dp_s"], dp["dp_t"], *cs, diverge_factor=100.0,
+                             repair_full_profile=r3)
     except (IndexError, ValueError) as e:
         r["st_exc"] = type(e).__name__
         return r
@@ -48,15 +50,20 @@ def _oracle_frame(sc, f, lat):
     return r
 
 
-@pytest.mark.parametrize("tag", ["A", "C"])
-def test_full_em_cycle_against_oracle_chain(tag):
+@pytest.mark.parametrize("tag,r3", [("A", False), ("C", False), ("A", True), ("C", True)])
+def test_full_em_cycle_against_oracle_chain(tag, r3):
+    """r3 = False: bug-compatible with the reference draft (full S-T profiles raise IndexError before the speed QP).
+    r3 = True: repair R3 (EmpSpeedQpParams.repair_full_profile): every frame of the 256-frame subsample that SURVEY
+    8(d) names runs the whole cycle, and every one of them is compared with the oracle chain."""
     import torch
     from emplanner_carla_b200 import api, scenes
     lat = scenes.LATTICES[tag]
-    B, NCHK = 256, 20 if tag == "A" else 10
+    B = 256
+    NCHK = (B if tag == "C" else 64) if r3 else (20 if tag == "A" else 10)
     sc = scenes.cycle_scenes(B, lat)
     dp = api.dp_params(**lat.kwargs())
-    cyc = api.EmCycle(B, dp, api.qp_params(), api.st_params(), api.speed_qp_params(), api.smooth_params())
+    cyc = api.EmCycle(B, dp, api.qp_params(), api.st_params(), api.speed_qp_params(repair_full_profile=r3),
+                      api.smooth_params())
     cu = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=np.float64)).cuda()
     st = sc["st"]
     b = cyc.run(cu(api.pack_scenes(**sc["sl"])), cu(api.pack_st_scenes(st["s_in"], st["s_out"], st["t_in"], st["t_out"], st["v0"])),
@@ -71,21 +78,21 @@ def test_full_em_cycle_against_oracle_chain(tag):
                       (view.qp_status == 0) & (h["convex_status"] == 0))[0]
     frames = sorted(set(range(NCHK)) | set(done[:NCHK].tolist()))
     for f in frames:
-        o = _oracle_frame(sc, f, lat)
+        o = _oracle_frame(sc, f, lat, r3)
         n = len(o["enr_s"])
         assert int(view.n_enr[f]) == n
         assert np.array_equal(view.enr_s[f, :n], o["enr_s"]) and np.abs(view.enr_l[f, :n] - o["enr_l"]).max() <= 1e-12
         if "qp_l" not in o:
             assert int(view.qp_status[f]) == api.QP_CORRIDOR_INDEX and h["npts"][f] == 0
             continue
-        if not o["qp_optimal"] or int(view.qp_status[f]) != 0:
-            continue
+        # the S-L QP is compared on every frame, converged or not (same divergence exit on both sides)
+        assert (int(view.qp_status[f]) == 0) == bool(o["qp_optimal"])
         m = len(o["qp_l"])
         assert np.sqrt(np.mean((view.qp_l[f, :m] - o["qp_l"]) ** 2)) <= 1e-4
-        assert h["npts"][f] == m + 1
+        assert h["npts"][f] == m + 2
         if o["smooth_optimal"] and h["smooth_status_iters"][f, 0] == 0:
-            assert np.abs(h["cart"][f, :m + 1, :2] - o["cart"][:, :2]).max() <= 1e-6
-            assert np.abs(h["cart"][f, :m + 1, 2:] - o["cart"][:, 2:]).max() <= 1e-5
+            assert np.abs(h["cart"][f, :m + 2, :2] - o["cart"][:, :2]).max() <= 1e-6
+            assert np.abs(h["cart"][f, :m + 2, 2:] - o["cart"][:, 2:]).max() <= 1e-5
         assert np.array_equal(h["st_out"][f, 8:24], o["dp_s"], equal_nan=True)
         assert np.array_equal(h["st_out"][f, 24:40], o["dp_t"], equal_nan=True)
         if "st_exc" in o:
@@ -105,7 +112,13 @@ def test_full_em_cycle_against_oracle_chain(tag):
         assert np.array_equal(~np.isnan(h["traj"][f]), ok)
         assert np.abs(h["traj"][f][ok] - o["traj"][ok]).max() <= 1e-4
         n_traj += 1
-    assert n_traj >= 3 and n_exc >= 1, (n_traj, n_exc)
+    if r3:
+        # every frame whose S-L QP converged runs the speed QP; the cycle finishes for the (large) majority
+        reached = (h["qp_status_iters"][:, 1] > 0).mean()
+        print("lattice", tag, "R3: frames compared end to end", n_traj, "of", len(frames), "reaching the speed QP %.2f" % reached)
+        assert n_traj >= (100 if tag == "C" else 30) and reached >= 0.6, (n_traj, reached)
+    else:
+        assert n_traj >= 3 and n_exc >= 1, (n_traj, n_exc)
     # whole-batch properties (size independent): time stamps increase, speed within the acceleration box's reach
     t = h["traj"][done]
     assert len(done) > 0 and np.all(np.diff(t[:, 6, :], axis=1) >= 0)
