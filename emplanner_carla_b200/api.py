@@ -54,8 +54,13 @@ def pack_scenes(obs_s, obs_l, nobs, s0, l0, dl0, ddl0, kmax=8):
     k_in = obs_s.shape[1]
     if k_in > kmax:
         raise ValueError("more obstacle slots (%d) than kmax (%d)" % (k_in, kmax))
-    rec[:, SCENE_HDR:SCENE_HDR + k_in] = np.nan_to_num(obs_s, nan=0.0)
-    rec[:, SCENE_HDR + kmax:SCENE_HDR + kmax + k_in] = np.nan_to_num(obs_l, nan=0.0)
+    # Slots at index >= K are padding (zeros; the kernels never read them).  A NaN INSIDE the first K slots stays a NaN:
+    # in the reference such an obstacle yields d2 = NaN, fails both range tests of cal_obs_cost (path_planning.py:601-608)
+    # and costs nothing, while the frame still takes the DP branch (len(obs_s_list) != 0, :362); the kernels' comparisons
+    # ignore it the same way (and cal_lmin_lmax's np.argmin of an all-NaN array is index 0, handled in sl_qp.cu).
+    live = np.arange(k_in)[None, :] < np.asarray(nobs).reshape(B, 1)
+    rec[:, SCENE_HDR:SCENE_HDR + k_in] = np.where(live, obs_s, 0.0)
+    rec[:, SCENE_HDR + kmax:SCENE_HDR + kmax + k_in] = np.where(live, obs_l, 0.0)
     return rec
 
 

@@ -197,9 +197,11 @@ qp_one_frame(const int frame, const int lane, const double *__restrict__ scenes,
                 const double ol = sc[EMP_SCENE_HDR + p.kmax + o];
                 const double smin = os - Q.obs_length / 2;
                 const double smax = os + Q.obs_length / 2;
-                const int lo = warp_argmin(valid0 ? fabs(dps - smin) : INF, lane) + 2;   // offset = 2 (:235,:240)
-                const int hi = warp_argmin(valid0 ? fabs(dps - smax) : INF, lane) + 2;
-                const int ctr = warp_argmin(valid0 ? fabs(dps - os) : INF, lane);
+                // np.argmin of an all-NaN array (NaN obstacle) is index 0
+                const bool os_nan = isnan(os);
+                const int lo = (os_nan ? 0 : warp_argmin(valid0 ? fabs(dps - smin) : INF, lane)) + 2;   // offset = 2 (:235,:240)
+                const int hi = (os_nan ? 0 : warp_argmin(valid0 ? fabs(dps - smax) : INF, lane)) + 2;
+                const int ctr = os_nan ? 0 : warp_argmin(valid0 ? fabs(dps - os) : INF, lane);
                 const double path_l = shfl(dpl, ctr);
                 if (lo <= hi && hi >= n) {         // the reference raises IndexError here (:265-272)
                     qp_status = EMP_QP_CORRIDOR_INDEX;
@@ -374,6 +376,9 @@ EMP_LEVEL_UNROLL
                 // eliminated at level t, so its D/CL/CR are dead afterwards and may be overwritten with garbage;
                 // remaining lanes only read from lanes eliminated at this level, and a missing left/right
                 // neighbour shows up as an exactly-zero coupling block (lane 31 is never a stage).
+                // The last level eliminates lane 15 alone: its neighbours (lane -1, lane 31) do not exist, so its
+                // coupling blocks are exactly zero and there is nobody to hand products to.
+                if (lev == EMP_CR_LEVELS - 1) break;
                 EMP_UNROLL
                 for (int r = 0; r < 3; ++r) {
                     EMP_UNROLL
@@ -437,7 +442,9 @@ EMP_LEVEL_UNROLL
                     ur1 = (F.xr[1] * t0 + F.xr[4] * t1) + F.xr[7] * t2;
                     ur2 = (F.xr[2] * t0 + F.xr[5] * t1) + F.xr[8] * t2;
                 }
-                // remaining lanes: r -= XR'(j-d) t(j-d) + XL'(j+d) t(j+d)   (dead values elsewhere, see factor)
+                // remaining lanes: r -= XR'(j-d) t(j-d) + XL'(j+d) t(j+d)   (dead values elsewhere, see factor);
+                // nobody remains after the last level (lane 15 alone, zero coupling blocks)
+                if (lev == EMP_CR_LEVELS - 1) break;
                 r0 -= shfl_up(ur0, d) + shfl_down(ul0, d);
                 r1 -= shfl_up(ur1, d) + shfl_down(ul1, d);
                 r2 -= shfl_up(ur2, d) + shfl_down(ul2, d);
@@ -448,8 +455,11 @@ EMP_LEVEL_UNROLL
             for (int lev = EMP_CR_LEVELS - 1; lev >= 0; --lev) {
                 const int d = 1 << lev, msk = 2 * d - 1;
                 const bool el = (lane & msk) == d - 1;
-                const double a0 = shfl_up(y0, d), a1 = shfl_up(y1, d), a2 = shfl_up(y2, d);
-                const double b0 = shfl_down(y0, d), b1 = shfl_down(y1, d), b2 = shfl_down(y2, d);
+                double a0 = 0.0, a1 = 0.0, a2 = 0.0, b0 = 0.0, b1 = 0.0, b2 = 0.0;
+                if (lev < EMP_CR_LEVELS - 1) {                   // the top level has no eliminated neighbours yet (y = 0)
+                    a0 = shfl_up(y0, d); a1 = shfl_up(y1, d); a2 = shfl_up(y2, d);
+                    b0 = shfl_down(y0, d); b1 = shfl_down(y1, d); b2 = shfl_down(y2, d);
+                }
                 if (el) {
                     const double v0 = t0 - (((F.xl[0] * a0 + F.xl[1] * a1) + F.xl[2] * a2) + ((F.xr[0] * b0 + F.xr[1] * b1) + F.xr[2] * b2));
                     const double v1 = t1 - (((F.xl[3] * a0 + F.xl[4] * a1) + F.xl[5] * a2) + ((F.xr[3] * b0 + F.xr[4] * b1) + F.xr[5] * b2));
@@ -502,8 +512,8 @@ EMP_LEVEL_UNROLL
         extern __shared__ double qp_smem[];
         double *sm_is = qp_smem + (size_t)(threadIdx.x >> 5) * (QP_SMEM_ROWS * 32) + lane;
         double *sm_iz = sm_is + NR * 32, *sm_rz = sm_iz + NR * 32, *sm_ws = sm_rz + NR * 32;
-        double *sm_xp = sm_ws + NR * 32;                           // iterate before the last step (divergence exit)
         double s[NR], z[NR], y[2] = {0.0, 0.0};
+        double *sm_xp = sm_ws + NR * 32;                           // iterate before the last step (divergence exit)
         double rx[3] = {0.0, 0.0, 0.0}, ry[2] = {0.0, 0.0};
         EMP_UNROLL
         for (int r = 0; r < NR; ++r) { s[r] = 1.0; z[r] = 1.0; sm_ws[r * 32] = 0.0; sm_rz[r * 32] = 0.0; }
@@ -516,7 +526,12 @@ EMP_LEVEL_UNROLL
                 pmul(x, pxq);
                 pxq[0] += q0;
                 atmul(y, aty);
-                gtmul(z, G, gtz);
+                {
+                    double zt[NR];
+                    EMP_UNROLL
+                    for (int r = 0; r < NR; ++r) zt[r] = z[r];
+                    gtmul(zt, G, gtz);
+                }
                 amul(x, ry);
                 gmul(x, G, gx);
                 double red[7] = {0, 0, 0, 0, 0, 0, 0};
@@ -597,8 +612,9 @@ EMP_LEVEL_UNROLL
                     const double sm_ = sigma * mu;
                     EMP_UNROLL
                     for (int r = 0; r < NR; ++r) {
-                        const double bs = (sm_ - s[r] * z[r]) - (pass == 1 ? sm_ws[r * 32] : 0.0);
-                        tq[r] = valid ? (bs + z[r] * sm_rz[r * 32]) * sm_is[r * 32] : 0.0;
+                        const double sr_ = s[r], zr_ = z[r];
+                        const double bs = (sm_ - sr_ * zr_) - (pass == 1 ? sm_ws[r * 32] : 0.0);
+                        tq[r] = valid ? (bs + zr_ * sm_rz[r * 32]) * sm_is[r * 32] : 0.0;
                     }
                     gtmul(tq, G, gtq);
                     EMP_UNROLL
@@ -614,10 +630,11 @@ EMP_LEVEL_UNROLL
                 const double sm_ = sigma * mu;
                 EMP_UNROLL
                 for (int r = 0; r < NR; ++r) {
+                    const double sr_ = s[r], zr_ = z[r];
                     const double isr = sm_is[r * 32], rzr = sm_rz[r * 32];
-                    const double bs = (sm_ - s[r] * z[r]) - (pass == 1 ? sm_ws[r * 32] : 0.0);
-                    const double tqr = (bs + z[r] * rzr) * isr;
-                    const double dzr = tqr + (z[r] * isr) * gdx[r];
+                    const double bs = (sm_ - sr_ * zr_) - (pass == 1 ? sm_ws[r * 32] : 0.0);
+                    const double tqr = (bs + zr_ * rzr) * isr;
+                    const double dzr = tqr + (zr_ * isr) * gdx[r];
                     const double dsr = -rzr - gdx[r];
                     if (valid) {
                         dsdz += dsr * dzr;
@@ -646,13 +663,15 @@ EMP_LEVEL_UNROLL
                 EMP_UNROLL
                 for (int r = 0; r < NR; ++r) {
                     const double hr = hrow(r);
-                    z[r] = valid ? gx[r] - hr : 1.0;
-                    s[r] = valid ? -z[r] : 1.0;
+                    const double z0 = valid ? gx[r] - hr : 1.0;
+                    const double s0 = valid ? -z0 : 1.0;
+                    z[r] = z0;
+                    s[r] = s0;
                     if (valid) {
-                        red[0] += s[r] * s[r];
+                        red[0] += s0 * s0;
                         red[2] += hr * hr;
-                        mn_s = fmax(mn_s, -s[r]);
-                        mn_z = fmax(mn_z, -z[r]);
+                        mn_s = fmax(mn_s, -s0);
+                        mn_z = fmax(mn_z, -z0);
                     }
                 }
                 warp_sum_n(red);
@@ -666,9 +685,12 @@ EMP_LEVEL_UNROLL
                 EMP_UNROLL
                 for (int r = 0; r < NR; ++r) {
                     if (valid) {
-                        if (sh_s != 0.0) s[r] += sh_s;
-                        if (sh_z != 0.0) z[r] += sh_z;
-                        gs += s[r] * z[r];
+                        double sr_ = s[r], zr_ = z[r];
+                        if (sh_s != 0.0) sr_ += sh_s;
+                        if (sh_z != 0.0) zr_ += sh_z;
+                        s[r] = sr_;
+                        z[r] = zr_;
+                        gs += sr_ * zr_;
                     }
                 }
                 gap = warp_sum(gs);
@@ -681,15 +703,18 @@ EMP_LEVEL_UNROLL
                 double gs = 0.0;
                 EMP_UNROLL
                 for (int r = 0; r < NR; ++r) {
+                    double sr_ = s[r], zr_ = z[r];
                     const double isr = sm_is[r * 32], rzr = sm_rz[r * 32];
-                    const double bs = (sm_ - s[r] * z[r]) - sm_ws[r * 32];
-                    const double tqr = (bs + z[r] * rzr) * isr;
-                    const double dzr = tqr + (z[r] * isr) * gdx[r];
+                    const double bs = (sm_ - sr_ * zr_) - sm_ws[r * 32];
+                    const double tqr = (bs + zr_ * rzr) * isr;
+                    const double dzr = tqr + (zr_ * isr) * gdx[r];
                     const double dsr = -rzr - gdx[r];
                     if (valid) {
-                        s[r] += step * dsr;
-                        z[r] += step * dzr;
-                        gs += s[r] * z[r];
+                        sr_ += step * dsr;
+                        zr_ += step * dzr;
+                        s[r] = sr_;
+                        z[r] = zr_;
+                        gs += sr_ * zr_;
                     }
                 }
                 EMP_UNROLL

@@ -117,14 +117,21 @@ def unpack_reply(buf):
     return dict(path=p, match_point_list=match, path_s=s, path_l=l, route_id=route_id)
 
 
-def stack_obstacles(requests, kmax=8):
+def stack_obstacles(requests, kmax=None):
     """Static obstacles of a list of unpacked requests -> (xy [B, kmax, 2] NaN padded, count [B]): the layout the
-    batched Frenet projection (HostPlanner.frenet_project) takes."""
+    batched Frenet projection (HostPlanner.frenet_project) takes.  kmax = None sizes the array for the largest request
+    (rounded up to an even slot count, at least 8).  A request with more obstacles than an explicit kmax is an error:
+    the reference plans around EVERY obstacle it is sent (test_9.py:116-122), so none is ever dropped silently."""
     B = len(requests)
+    most = max([len(r["static_obs_info"]) for r in requests], default=0)
+    if kmax is None:
+        kmax = max(8, most + (most & 1))
+    elif most > kmax:
+        raise WireError("a request carries %d static obstacles but only %d slots were asked for" % (most, kmax))
     xy = np.full((B, kmax, 2), np.nan)
     n = np.zeros(B, dtype=np.int32)
     for b, r in enumerate(requests):
-        k = min(len(r["static_obs_info"]), kmax)
+        k = len(r["static_obs_info"])
         xy[b, :k] = r["static_obs_info"][:k, :2]
         n[b] = k
     return xy, n

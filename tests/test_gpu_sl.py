@@ -278,3 +278,39 @@ def test_dp_bit_exact_at_scale_and_at_the_lattice_limits(planner):
     for b in range(B):
         es, el = sl_dp.enrich(o_s[b], o_l[b], s0[b], l0[b], dl0[b], ddl0[b], resolution=1)
         assert int(view.n_enr[b]) == len(es) and np.abs(view.enr_l[b, :len(es)] - el).max() <= 1e-12
+
+
+def test_nan_obstacle_inside_the_list_is_ignored_like_in_the_reference(planner):
+    """A NaN obstacle among the first K costs nothing in cal_obs_cost (both range tests fail, path_planning.py:601-608)
+    but the frame still takes the DP branch; cal_lmin_lmax sees np.argmin of an all-NaN array (= 0).  The scene record
+    keeps the NaN (api.pack_scenes) and the kernels must behave like the oracle on the same arrays."""
+    from emplanner_carla_b200 import api, scenes
+    from oracle import sl_dp, sl_qp
+    lat = scenes.LATTICE_A
+    sc = scenes.sl_scenes(64, lat, 77, k_fixed=3)
+    sc["obs_s"][:, 1] = np.nan
+    sc["obs_l"][:, 1] = np.nan
+    sc["obs_s"][:8, 0] = np.nan                                 # some frames: only the s of an obstacle is NaN
+    sc["nobs"][60:] = 1
+    sc["obs_s"][60:, 0] = np.nan                                # frames whose ONLY obstacle is NaN: DP branch, zero obstacle cost
+    sc["obs_l"][60:, 0] = np.nan
+    dp, qp = api.dp_params(**lat.kwargs()), api.qp_params()
+    rec = api.pack_scenes(**sc)
+    assert np.isnan(rec[:60, 7]).all() and not np.isnan(rec[:, 8]).any() and np.all(rec[60:, 7] == 0.0)
+    view, rows = planner.plan(rec, dp, qp, want_rows=True)
+    o_rows, o_s, o_l, o_cost = sl_dp.dp_batch(sc["obs_s"], sc["obs_l"], sc["nobs"], sc["s0"], sc["l0"], sc["dl0"],
+                                              sc["ddl0"], **lat.kwargs())
+    assert np.array_equal(rows, o_rows) and np.array_equal(view.dp_cost, o_cost)
+    assert np.all(rows[60:] >= 0)                               # not the K == 0 straight branch
+    for b in range(64):
+        K = int(sc["nobs"][b])
+        es, el = sl_dp.enrich(o_s[b], o_l[b], sc["s0"][b], sc["l0"][b], sc["dl0"][b], sc["ddl0"][b], lat.sampling_res)
+        try:
+            lmin, lmax = sl_qp.corridor(es[::2], el[::2], sc["obs_s"][b, :K], sc["obs_l"][b, :K], 5, 5)
+        except IndexError:
+            assert int(view.qp_status[b]) == api.QP_CORRIDOR_INDEX
+            continue
+        l, _, _, info = sl_qp.quadratic_planning(lmin, lmax, sc["l0"][b], sc["dl0"][b], sc["ddl0"][b], diverge_factor=2.0)
+        assert (info["status"] == "optimal") == (int(view.qp_status[b]) == 0)
+        m = len(l)
+        assert np.sqrt(np.mean((view.qp_l[b, :m] - l) ** 2)) <= 1e-4

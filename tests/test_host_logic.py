@@ -43,7 +43,7 @@ def test_argument_errors_are_reported_not_crashed():
     from emplanner_carla_b200 import _lib
     lib = _lib.lib()
     d = _lib.dp_params(row=40)
-    rc = lib.emp_sl_dp_dev(None, 8, 4, ctypes.byref(d), 49, None, None, None)
+    rc = lib.emp_sl_dp_dev(None, 8, 4, ctypes.byref(d), 49, None, None, None, None)
     assert rc < 0 and b"row" in lib.emp_last_error()
     with pytest.raises(_lib.EmpError):
         _lib.check(rc)
@@ -125,6 +125,9 @@ def test_wire_format_round_trip_and_errors():
     assert np.array_equal(rep["path"], path) and list(rep["match_point_list"]) == [17, 3] and rep["path_l"][5] == -5.0
     xy, n = wire.stack_obstacles([r, r2], kmax=4)
     assert xy.shape == (2, 4, 2) and list(n) == [2, 0] and xy[0, 1, 1] == -4.25 and np.isnan(xy[1]).all()
+    assert wire.stack_obstacles([r, r2])[0].shape == (2, 8, 2)
+    with pytest.raises(wire.WireError):                       # never drop an obstacle silently
+        wire.stack_obstacles([r, r2], kmax=1)
 
 
 def test_speed_qp_kernel_linear_algebra_model_reproduces_the_oracle_iterates():

@@ -47,6 +47,8 @@ rec = api.pack_scenes(**sc)
 K = sc["nobs"]
 run("benchmark batch, natural order", rec)
 run("benchmark batch, emp_sl_order_dev schedule", rec, scheduled=True)
+if "--quick" in sys.argv:
+    sys.exit(0)
 order = np.argsort(-K, kind="stable")
 run("sorted by K descending", rec[order])
 N = 1024
