@@ -548,8 +548,8 @@ class EmCycle:
         self.sl_kmax, self.st_kmax = int(sl_kmax), int(st_kmax)
         self.NE = max_enriched(dp)
         self.MP = (self.NE + 1) // 2 + 2                  # plan start + mid-point path: n_qp + 2 points (path_planning.py:31-34)
-        if self.MP > 64:
-            raise ValueError("path of %d points exceeds the 64 points of the reference-line smoother" % self.MP)
+        if self.MP > 128:
+            raise ValueError("path of %d points exceeds the 128 points of the reference-line smoother" % self.MP)
         self.NP = self.MP + 1                             # + NaN terminator (speed_planning_test.py:581)
         dev = device if device is not None else torch.device("cuda", torch.cuda.current_device())
         f64 = lambda *s: torch.zeros(s, dtype=torch.float64, device=dev)

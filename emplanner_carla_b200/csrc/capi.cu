@@ -97,6 +97,7 @@ int make_qp_launch(emp::QpLaunch &L, const EmpQpParams *p, int kmax, int batch, 
     L.plan_stride = emp_plan_stride(n_enr_max);
     L.n_enr_max = n_enr_max;
     L.n_direct = n_direct;
+    L.n_fused_max = (n_enr_max + 1) / 2;
     L.mode = mode;
     L.order = nullptr;
     L.n_peers = 0;
@@ -224,12 +225,26 @@ int emp_sl_dp_dev(const double *scenes, int kmax, int batch, const EmpDpParams *
     return e == cudaSuccess ? 0 : fail_cuda(e, "sl_dp launch");
 }
 
+namespace {
+// FUSED-mode launches issued right after a DP launch know the lattice: the densified path has at most
+// emp_max_enriched(dp) points, which bounds the QP stations tighter than the record capacity n_enr_max does.
+thread_local int g_fused_station_bound = 0;
+struct FusedBound {
+    explicit FusedBound(const EmpDpParams *dp) { g_fused_station_bound = dp ? (emp_max_enriched(dp) + 1) / 2 : 0; }
+    ~FusedBound() { g_fused_station_bound = 0; }
+};
+void apply_fused_bound(emp::QpLaunch &L) {
+    if (g_fused_station_bound > 0 && g_fused_station_bound < L.n_fused_max) L.n_fused_max = g_fused_station_bound;
+}
+}  // namespace
+
 int emp_sl_qp_dev(const double *scenes, int kmax, int batch, const EmpQpParams *p, int n_enr_max,
                   double *plans, double *lmin_lmax, const int32_t *order, void *stream) {
     emp::QpLaunch L;
     if (int rc = make_qp_launch(L, p, kmax, batch, n_enr_max, 0, emp::QP_MODE_FUSED)) return rc;
     if (batch == 0) return 0;
     if (!scenes || !plans) return fail(-1, "scenes/plans is NULL");
+    apply_fused_bound(L);
     L.order = order;
     cudaError_t e = emp::launch_sl_qp(scenes, plans, lmin_lmax, nullptr, nullptr, nullptr, nullptr, nullptr, L,
                                       (cudaStream_t)stream);
@@ -265,6 +280,7 @@ int emp_sl_plan_dev(const double *scenes, int kmax, int batch, const EmpDpParams
     if (order_ws)
         if (int rc = emp_sl_order_dev(scenes, kmax, batch, order_ws, stream)) return rc;
     if (int rc = emp_sl_dp_dev(scenes, kmax, batch, dp, n_enr_max, plans, rows, order_ws, stream)) return rc;
+    FusedBound bound(dp);
     return emp_sl_qp_dev(scenes, kmax, batch, qp, n_enr_max, plans, nullptr, order_ws, stream);
 }
 
@@ -332,6 +348,7 @@ int emp_sl_qp_p2p_dev(const double *scenes, int kmax, int batch, const EmpQpPara
     if (int rc = make_qp_launch(L, qp, kmax, batch, n_enr_max, 0, emp::QP_MODE_FUSED)) return rc;
     if (batch == 0) return 0;
     if (!scenes || !plans) return fail(-1, "scenes/plans is NULL");
+    apply_fused_bound(L);
     L.n_peers = n_peers;
     L.order = order;
     for (int r = 0; r < n_peers; ++r) {
@@ -384,6 +401,7 @@ int emp_sl_plan_p2p_dev(const double *scenes, int kmax, int batch, const EmpDpPa
     if (order_ws)
         if (int rc = emp_sl_order_dev(scenes, kmax, batch, order_ws, stream)) return rc;
     if (int rc = emp_sl_dp_dev(scenes, kmax, batch, dp, n_enr_max, plans, rows, order_ws, stream)) return rc;
+    FusedBound bound(dp);
     return emp_sl_qp_p2p_dev(scenes, kmax, batch, qp, n_enr_max, plans, n_peers, peer_slices, order_ws, stream);
 }
 
@@ -515,6 +533,7 @@ static int plan_host_impl(EmpPlanner *pl, const double *scenes, int batch, const
                        pl->stream);
     if (rc) return rc;
     if (qp) {
+        FusedBound bound(dp);
         rc = emp_sl_qp_dev(pl->d_scenes, pl->kmax, batch, qp, pl->n_enr_max, pl->d_plans, nullptr, pl->d_order, pl->stream);
         if (rc) return rc;
     }

@@ -36,6 +36,7 @@ struct QpLaunch {
     EmpQpParams q;
     int batch, kmax, scene_stride, plan_stride, n_enr_max;
     int n_direct;             // stations per frame in the DIRECT / CORRIDOR modes
+    int n_fused_max;          // FUSED mode: upper bound on the stations of any frame (selects the warp / block path)
     int mode;                 // QP_MODE_*
     const int32_t *order;     // optional [batch]: ticket -> frame, heaviest frames first (launch_sl_order)
     int n_peers;              // fused all-gather: number of peer slices to push each plan record to

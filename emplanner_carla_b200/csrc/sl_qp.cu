@@ -70,30 +70,6 @@ __device__ __forceinline__ void gtmul(const double v[NR], const Geo &G, double o
     o[2] = v[10] - v[13];
 }
 
-template <int N>
-__device__ __forceinline__ void warp_sum_n(double (&v)[N]) {
-    EMP_UNROLL
-    for (int o = 16; o > 0; o >>= 1) {
-        EMP_UNROLL
-        for (int k = 0; k < N; ++k) v[k] += shfl_xor(v[k], o);
-    }
-}
-
-// first-minimum argmin over lanes (np.argmin semantics)
-__device__ __forceinline__ int warp_argmin(double v, int lane) {
-    int idx = lane;
-    EMP_UNROLL
-    for (int o = 16; o > 0; o >>= 1) {
-        const double ov = shfl_xor(v, o);
-        const int oi = __shfl_xor_sync(EMP_FULL_MASK, idx, o);
-        if (ov < v || (ov == v && oi < idx)) {
-            v = ov;
-            idx = oi;
-        }
-    }
-    return idx;
-}
-
 // 1/x and 1/sqrt(x) for positive, normal-range x: hardware seed + two Newton steps (no special-case paths).
 __device__ __forceinline__ double frcp(double x) {
     double y;
@@ -136,11 +112,18 @@ struct Factor {                 // per-lane pieces of the KKT factorisation
 
 // One frame, one warp.  Everything below is warp-local (registers, shuffles, this warp's slice of shared memory),
 // so the warps of a CTA are independent workers.
+template <int NL>
 __device__ __forceinline__ void
 qp_one_frame(const int frame, const int lane, const double *__restrict__ scenes, double *__restrict__ plans,
              double *__restrict__ lmin_lmax, const double *__restrict__ lmin_in, const double *__restrict__ lmax_in,
              const double *__restrict__ start_in, double *__restrict__ out_x, int32_t *__restrict__ status_iters,
              const QpLaunch &p) {
+    constexpr int LEVELS = NL == 32 ? 5 : (NL == 64 ? 6 : 7);   // cyclic-reduction levels = log2(lanes)
+    // shared memory: per frame QP_SMEM_ROWS rows of NL doubles ([row][lane]); the warp path has QP_WARPS frames per CTA,
+    // the block path one frame plus the two exchange lines of Lanes<NL>
+    extern __shared__ double qp_smem_all[];
+    double *qp_smem = qp_smem_all + (NL == 32 ? (size_t)(threadIdx.x >> 5) * (QP_SMEM_ROWS * 32) : (size_t)0);
+    Lanes<NL> L(lane, qp_smem_all + QP_SMEM_ROWS * NL);
     const EmpQpParams &Q = p.q;
 
     // ---------------- inputs ---------------------------------------------------
@@ -151,7 +134,7 @@ qp_one_frame(const int frame, const int lane, const double *__restrict__ scenes,
     double *plan = nullptr;
     if (p.mode == QP_MODE_DIRECT) {
         n = p.n_direct;
-        if (n > EMP_MAX_QP_POINTS || n < 2) qp_status = EMP_QP_TOO_LARGE;
+        if (n > NL || n < 2) qp_status = EMP_QP_TOO_LARGE;
         if (lane < n && qp_status == EMP_QP_OK) {
             lmin = lmin_in[(size_t)frame * n + lane];
             lmax = lmax_in[(size_t)frame * n + lane];
@@ -176,7 +159,7 @@ qp_one_frame(const int frame, const int lane, const double *__restrict__ scenes,
             n = p.n_direct;
             nq_out = n;
         }
-        if (n > EMP_MAX_QP_POINTS || n < (p.mode == QP_MODE_FUSED ? 2 : 1)) qp_status = EMP_QP_TOO_LARGE;
+        if (n > NL || n < (p.mode == QP_MODE_FUSED ? 2 : 1)) qp_status = EMP_QP_TOO_LARGE;
         const bool valid0 = lane < n && qp_status == EMP_QP_OK;
         if (valid0) {
             if (p.mode == QP_MODE_FUSED) {
@@ -199,10 +182,10 @@ qp_one_frame(const int frame, const int lane, const double *__restrict__ scenes,
                 const double smax = os + Q.obs_length / 2;
                 // np.argmin of an all-NaN array (NaN obstacle) is index 0
                 const bool os_nan = isnan(os);
-                const int lo = (os_nan ? 0 : warp_argmin(valid0 ? fabs(dps - smin) : INF, lane)) + 2;   // offset = 2 (:235,:240)
-                const int hi = (os_nan ? 0 : warp_argmin(valid0 ? fabs(dps - smax) : INF, lane)) + 2;
-                const int ctr = os_nan ? 0 : warp_argmin(valid0 ? fabs(dps - os) : INF, lane);
-                const double path_l = shfl(dpl, ctr);
+                const int lo = (os_nan ? 0 : L.argmin(valid0 ? fabs(dps - smin) : INF)) + 2;   // offset = 2 (:235,:240)
+                const int hi = (os_nan ? 0 : L.argmin(valid0 ? fabs(dps - smax) : INF)) + 2;
+                const int ctr = os_nan ? 0 : L.argmin(valid0 ? fabs(dps - os) : INF);
+                const double path_l = L.get(dpl, ctr);
                 if (lo <= hi && hi >= n) {         // the reference raises IndexError here (:265-272)
                     qp_status = EMP_QP_CORRIDOR_INDEX;
                     break;
@@ -244,8 +227,8 @@ qp_one_frame(const int frame, const int lane, const double *__restrict__ scenes,
         G.e = ds / 2;
         G.g0 = ds * ds / 6;
         const int fi = (int)ceil(Q.host_d1 / ds), bi = (int)ceil(Q.host_d2 / ds);
-        const double hU = shfl(lmax, min(lane + fi, n - 1));     // l_max[index1] (:130)
-        const double hL = shfl(lmin, max(lane - bi, 0));         // l_min[index2] (:131)
+        const double hU = L.get(lmax, min(lane + fi, n - 1));     // l_max[index1] (:130)
+        const double hL = L.get(lmin, max(lane - bi, 0));         // l_min[index2] (:131)
         const double hw = Q.host_w / 2;
         // h is recomputed from 5 registers where it is needed (:133-166): rows 0-7 from the corridor, rows 8-13
         // from the +-1e5 boxes, pinned to the plan start on lane 0 (:148-153) and to 0 on lane n-1 (:155-160)
@@ -324,12 +307,12 @@ qp_one_frame(const int frame, const int lane, const double *__restrict__ scenes,
                 B[2] = B[5] = B[6] = B[7] = B[8] = 0.0;
             }
             // K_ii = E X_i E' + F X_{i+1} F' + diag(0,0,1/(2 w_dddl))
-            const double k00 = e00 + shfl_down(f00, 1);
-            const double k10 = e10 + shfl_down(f10, 1);
-            const double k11 = e11 + shfl_down(f11, 1);
-            const double k20 = e20 + shfl_down(f20, 1);
-            const double k21 = e21 + shfl_down(f21, 1);
-            const double k22 = (e22 + shfl_down(f22, 1)) + jinv;
+            const double k00 = e00 + L.down(f00, 1);
+            const double k10 = e10 + L.down(f10, 1);
+            const double k11 = e11 + L.down(f11, 1);
+            const double k20 = e20 + L.down(f20, 1);
+            const double k21 = e21 + L.down(f21, 1);
+            const double k22 = (e22 + L.down(f22, 1)) + jinv;
             // pivot block D, couplings CL = K(i, i-1) = B', CR = K(i, i+1) = B of the next lane
             double D00 = k00, D10 = k10, D11 = k11, D20 = k20, D21 = k21, D22 = k22;
             double CL[9], CR[9];
@@ -338,7 +321,7 @@ qp_one_frame(const int frame, const int lane, const double *__restrict__ scenes,
                 EMP_UNROLL
                 for (int c = 0; c < 3; ++c) {
                     CL[3 * r + c] = (stage && lane > 0) ? B[3 * c + r] : 0.0;
-                    const double nb = shfl_down(B[3 * r + c], 1);
+                    const double nb = L.down(B[3 * r + c], 1);
                     CR[3 * r + c] = (lane < n - 2) ? nb : 0.0;
                 }
             }
@@ -347,7 +330,7 @@ qp_one_frame(const int frame, const int lane, const double *__restrict__ scenes,
             EMP_UNROLL
             for (int k = 0; k < 9; ++k) { F.xl[k] = 0.0; F.xr[k] = 0.0; }
 EMP_LEVEL_UNROLL
-            for (int lev = 0; lev < EMP_CR_LEVELS; ++lev) {
+            for (int lev = 0; lev < LEVELS; ++lev) {
                 const int d = 1 << lev, msk = 2 * d - 1;
                 const bool el = (lane & msk) == d - 1;
                 if (el) {
@@ -378,18 +361,18 @@ EMP_LEVEL_UNROLL
                 // neighbour shows up as an exactly-zero coupling block (lane 31 is never a stage).
                 // The last level eliminates lane 15 alone: its neighbours (lane -1, lane 31) do not exist, so its
                 // coupling blocks are exactly zero and there is nobody to hand products to.
-                if (lev == EMP_CR_LEVELS - 1) break;
+                if (lev == LEVELS - 1) break;
                 EMP_UNROLL
                 for (int r = 0; r < 3; ++r) {
                     EMP_UNROLL
                     for (int c = 0; c < 3; ++c) {
                         const double plr = (F.xl[r] * F.xr[c] + F.xl[3 + r] * F.xr[3 + c]) + F.xl[6 + r] * F.xr[6 + c];
-                        CL[3 * c + r] = -shfl_up(plr, d);         // K(j, j-2d) = -(XL'XR of lane j-d)'
-                        CR[3 * r + c] = -shfl_down(plr, d);       // K(j, j+2d) = -(XL'XR of lane j+d)
+                        CL[3 * c + r] = -L.up(plr, d);         // K(j, j-2d) = -(XL'XR of lane j-d)'
+                        CR[3 * r + c] = -L.down(plr, d);       // K(j, j+2d) = -(XL'XR of lane j+d)
                         if (c <= r) {
                             const double prr = (F.xr[r] * F.xr[c] + F.xr[3 + r] * F.xr[3 + c]) + F.xr[6 + r] * F.xr[6 + c];
                             const double pll = (F.xl[r] * F.xl[c] + F.xl[3 + r] * F.xl[3 + c]) + F.xl[6 + r] * F.xl[6 + c];
-                            const double upd = shfl_up(prr, d) + shfl_down(pll, d);   // (XR'XR)(j-d) + (XL'XL)(j+d)
+                            const double upd = L.up(prr, d) + L.down(pll, d);   // (XR'XR)(j-d) + (XL'XL)(j+d)
                             if (r == 0) D00 -= upd;
                             else if (r == 1 && c == 0) D10 -= upd;
                             else if (r == 1) D11 -= upd;
@@ -400,7 +383,7 @@ EMP_LEVEL_UNROLL
                     }
                 }
             }
-            broke = __any_sync(EMP_FULL_MASK, bad);
+            broke = L.any(bad);
         };
 
         // solve [S A'; A 0][dx; dy] = [g; by] with the current factorisation
@@ -420,14 +403,14 @@ EMP_LEVEL_UNROLL
             const double fx0 = -xg[0] + G.g0 * xg[2];
             const double fx1 = -xg[1] + G.e * xg[2];
             const double fx2 = -xg[2];
-            double r0 = ((xg[0] + G.a * xg[1]) + G.b * xg[2]) + shfl_down(fx0, 1) - by[0];
-            double r1 = (xg[1] + G.e * xg[2]) + shfl_down(fx1, 1) - by[1];
-            double r2 = nojerk ? 0.0 : xg[2] + shfl_down(fx2, 1);
+            double r0 = ((xg[0] + G.a * xg[1]) + G.b * xg[2]) + L.down(fx0, 1) - by[0];
+            double r1 = (xg[1] + G.e * xg[2]) + L.down(fx1, 1) - by[1];
+            double r2 = nojerk ? 0.0 : xg[2] + L.down(fx2, 1);
             // forward elimination, level by level: t_i = L_i^-1 r_i, then r_{i-d} -= XL' t_i, r_{i+d} -= XR' t_i
             if (!stage) { r0 = 0.0; r1 = 0.0; r2 = 0.0; }
             double t0 = 0.0, t1 = 0.0, t2 = 0.0;
 EMP_LEVEL_UNROLL
-            for (int lev = 0; lev < EMP_CR_LEVELS; ++lev) {
+            for (int lev = 0; lev < LEVELS; ++lev) {
                 const int d = 1 << lev, msk = 2 * d - 1;
                 const bool el = (lane & msk) == d - 1;
                 double ul0 = 0.0, ul1 = 0.0, ul2 = 0.0, ur0 = 0.0, ur1 = 0.0, ur2 = 0.0;
@@ -444,21 +427,21 @@ EMP_LEVEL_UNROLL
                 }
                 // remaining lanes: r -= XR'(j-d) t(j-d) + XL'(j+d) t(j+d)   (dead values elsewhere, see factor);
                 // nobody remains after the last level (lane 15 alone, zero coupling blocks)
-                if (lev == EMP_CR_LEVELS - 1) break;
-                r0 -= shfl_up(ur0, d) + shfl_down(ul0, d);
-                r1 -= shfl_up(ur1, d) + shfl_down(ul1, d);
-                r2 -= shfl_up(ur2, d) + shfl_down(ul2, d);
+                if (lev == LEVELS - 1) break;
+                r0 -= L.up(ur0, d) + L.down(ul0, d);
+                r1 -= L.up(ur1, d) + L.down(ul1, d);
+                r2 -= L.up(ur2, d) + L.down(ul2, d);
             }
             // back substitution, top level first: y_i = L_i^-T (t_i - XL y_{i-d} - XR y_{i+d})
             double y0 = 0.0, y1 = 0.0, y2 = 0.0;
 EMP_LEVEL_UNROLL
-            for (int lev = EMP_CR_LEVELS - 1; lev >= 0; --lev) {
+            for (int lev = LEVELS - 1; lev >= 0; --lev) {
                 const int d = 1 << lev, msk = 2 * d - 1;
                 const bool el = (lane & msk) == d - 1;
                 double a0 = 0.0, a1 = 0.0, a2 = 0.0, b0 = 0.0, b1 = 0.0, b2 = 0.0;
-                if (lev < EMP_CR_LEVELS - 1) {                   // the top level has no eliminated neighbours yet (y = 0)
-                    a0 = shfl_up(y0, d); a1 = shfl_up(y1, d); a2 = shfl_up(y2, d);
-                    b0 = shfl_down(y0, d); b1 = shfl_down(y1, d); b2 = shfl_down(y2, d);
+                if (lev < LEVELS - 1) {                   // the top level has no eliminated neighbours yet (y = 0)
+                    a0 = L.up(y0, d); a1 = L.up(y1, d); a2 = L.up(y2, d);
+                    b0 = L.down(y0, d); b1 = L.down(y1, d); b2 = L.down(y2, d);
                 }
                 if (el) {
                     const double v0 = t0 - (((F.xl[0] * a0 + F.xl[1] * a1) + F.xl[2] * a2) + ((F.xr[0] * b0 + F.xr[1] * b1) + F.xr[2] * b2));
@@ -471,7 +454,7 @@ EMP_LEVEL_UNROLL
             }
             if (!stage) { y0 = 0.0; y1 = 0.0; y2 = 0.0; }
             // x = X (g - E' y_i - F' y_{i-1})
-            double pu0 = shfl_up(y0, 1), pu1 = shfl_up(y1, 1), pu2 = shfl_up(y2, 1);
+            double pu0 = L.up(y0, 1), pu1 = L.up(y1, 1), pu2 = L.up(y2, 1);
             if (lane == 0) { pu0 = 0.0; pu1 = 0.0; pu2 = 0.0; }
             double v[3];
             v[0] = g[0] - (y0 - pu0);
@@ -484,7 +467,7 @@ EMP_LEVEL_UNROLL
 
         // P x (with the jerk coupling), A x, A' y
         auto pmul = [&](const double xx[3], double o[3]) {
-            double up = shfl_up(xx[2], 1), dn = shfl_down(xx[2], 1);
+            double up = L.up(xx[2], 1), dn = L.down(xx[2], 1);
             if (lane == 0) up = 0.0;
             if (lane >= n - 1) dn = 0.0;
             o[0] = Pd[0] * xx[0];
@@ -492,12 +475,12 @@ EMP_LEVEL_UNROLL
             o[2] = Pd[2] * xx[2] + cc * (up + dn);
         };
         auto amul = [&](const double xx[3], double o[2]) {
-            const double n0 = shfl_down(xx[0], 1), n1 = shfl_down(xx[1], 1), n2 = shfl_down(xx[2], 1);
+            const double n0 = L.down(xx[0], 1), n1 = L.down(xx[1], 1), n2 = L.down(xx[2], 1);
             o[0] = stage ? (((xx[0] + G.a * xx[1]) + G.b * xx[2]) - n0) + G.g0 * n2 : 0.0;
             o[1] = stage ? ((xx[1] + G.e * xx[2]) - n1) + G.e * n2 : 0.0;
         };
         auto atmul = [&](const double yy[2], double o[3]) {
-            double p0 = shfl_up(yy[0], 1), p1 = shfl_up(yy[1], 1);
+            double p0 = L.up(yy[0], 1), p1 = L.up(yy[1], 1);
             if (lane == 0) { p0 = 0.0; p1 = 0.0; }
             o[0] = yy[0] - p0;
             o[1] = (G.a * yy[0] + yy[1]) - p1;
@@ -509,14 +492,13 @@ EMP_LEVEL_UNROLL
         // (two solves), so factor() and kkt_solve() are instantiated once (code size: instruction cache).
         // Per-row state: s, z live in registers; 1/s, 1/z, rz and the predictor's ds o dz live in shared
         // memory ([row][lane], conflict-free); everything else per row is recomputed where it is used.
-        extern __shared__ double qp_smem[];
-        double *sm_is = qp_smem + (size_t)(threadIdx.x >> 5) * (QP_SMEM_ROWS * 32) + lane;
-        double *sm_iz = sm_is + NR * 32, *sm_rz = sm_iz + NR * 32, *sm_ws = sm_rz + NR * 32;
+        double *sm_is = qp_smem + lane;                            // this frame's rows, [row][lane]
+        double *sm_iz = sm_is + NR * NL, *sm_rz = sm_iz + NR * NL, *sm_ws = sm_rz + NR * NL;
         double s[NR], z[NR], y[2] = {0.0, 0.0};
-        double *sm_xp = sm_ws + NR * 32;                           // iterate before the last step (divergence exit)
+        double *sm_xp = sm_ws + NR * NL;                           // iterate before the last step (divergence exit)
         double rx[3] = {0.0, 0.0, 0.0}, ry[2] = {0.0, 0.0};
         EMP_UNROLL
-        for (int r = 0; r < NR; ++r) { s[r] = 1.0; z[r] = 1.0; sm_ws[r * 32] = 0.0; sm_rz[r * 32] = 0.0; }
+        for (int r = 0; r < NR; ++r) { s[r] = 1.0; z[r] = 1.0; sm_ws[r * NL] = 0.0; sm_rz[r * NL] = 0.0; }
         double resx0 = 1.0, resz0 = 1.0, gap_min = 0.0;
         const double resy0 = 1.0;                                  // b = 0
         int it = -1;
@@ -547,11 +529,11 @@ EMP_LEVEL_UNROLL
                 EMP_UNROLL
                 for (int r = 0; r < NR; ++r) {
                     const double rzr = valid ? (s[r] + gx[r]) - hrow(r) : 0.0;
-                    sm_rz[r * 32] = rzr;
+                    sm_rz[r * NL] = rzr;
                     red[2] += rzr * rzr;
                     red[6] += valid ? z[r] * rzr : 0.0;
                 }
-                warp_sum_n(red);
+                L.sum_n(red);
                 const double resx = sqrt(red[0]), resy = sqrt(red[1]), resz = sqrt(red[2]);
                 const double pcost = 0.5 * (red[3] + red[4]);
                 const double dcost = ((pcost + red[5]) + red[6]) - gap;
@@ -570,11 +552,11 @@ EMP_LEVEL_UNROLL
                 // The gap of a converging solve decreases monotonically, so the first clear increase ends the solve.
                 if (it > 0 && Q.diverge_factor > 0.0 && gap > Q.diverge_factor * gap_min) {
                     qp_status = EMP_QP_UNKNOWN_DIVERGED;           // the step that blew the gap up is discarded
-                    x[0] = sm_xp[0]; x[1] = sm_xp[32]; x[2] = sm_xp[64];
+                    x[0] = sm_xp[0]; x[1] = sm_xp[NL]; x[2] = sm_xp[2 * NL];
                     break;
                 }
                 gap_min = fmin(gap_min, gap);
-                sm_xp[0] = x[0]; sm_xp[32] = x[1]; sm_xp[64] = x[2];
+                sm_xp[0] = x[0]; sm_xp[NL] = x[1]; sm_xp[2 * NL] = x[2];
             }
 
             {
@@ -582,8 +564,8 @@ EMP_LEVEL_UNROLL
                 EMP_UNROLL
                 for (int r = 0; r < NR; ++r) {
                     const double isr = frcp(s[r]);
-                    sm_is[r * 32] = isr;
-                    sm_iz[r * 32] = frcp(z[r]);
+                    sm_is[r * NL] = isr;
+                    sm_iz[r * NL] = frcp(z[r]);
                     w[r] = z[r] * isr;
                 }
                 factor(w);
@@ -613,8 +595,8 @@ EMP_LEVEL_UNROLL
                     EMP_UNROLL
                     for (int r = 0; r < NR; ++r) {
                         const double sr_ = s[r], zr_ = z[r];
-                        const double bs = (sm_ - sr_ * zr_) - (pass == 1 ? sm_ws[r * 32] : 0.0);
-                        tq[r] = valid ? (bs + zr_ * sm_rz[r * 32]) * sm_is[r * 32] : 0.0;
+                        const double bs = (sm_ - sr_ * zr_) - (pass == 1 ? sm_ws[r * NL] : 0.0);
+                        tq[r] = valid ? (bs + zr_ * sm_rz[r * NL]) * sm_is[r * NL] : 0.0;
                     }
                     gtmul(tq, G, gtq);
                     EMP_UNROLL
@@ -631,20 +613,20 @@ EMP_LEVEL_UNROLL
                 EMP_UNROLL
                 for (int r = 0; r < NR; ++r) {
                     const double sr_ = s[r], zr_ = z[r];
-                    const double isr = sm_is[r * 32], rzr = sm_rz[r * 32];
-                    const double bs = (sm_ - sr_ * zr_) - (pass == 1 ? sm_ws[r * 32] : 0.0);
+                    const double isr = sm_is[r * NL], rzr = sm_rz[r * NL];
+                    const double bs = (sm_ - sr_ * zr_) - (pass == 1 ? sm_ws[r * NL] : 0.0);
                     const double tqr = (bs + zr_ * rzr) * isr;
                     const double dzr = tqr + (zr_ * isr) * gdx[r];
                     const double dsr = -rzr - gdx[r];
                     if (valid) {
                         dsdz += dsr * dzr;
                         ts = fmax(ts, -dsr * isr);
-                        tz = fmax(tz, -dzr * sm_iz[r * 32]);
+                        tz = fmax(tz, -dzr * sm_iz[r * NL]);
                     }
-                    if (pass == 0) sm_ws[r * 32] = dsr * dzr;
+                    if (pass == 0) sm_ws[r * NL] = dsr * dzr;
                 }
-                dsdz = warp_sum(dsdz);
-                const double t = fmax(0.0, warp_max(fmax(ts, tz)));
+                dsdz = L.sum(dsdz);
+                const double t = fmax(0.0, L.max(fmax(ts, tz)));
                 if (t == 0.0) step = 1.0;
                 else step = pass == 0 ? fmin(1.0, 1.0 / t) : fmin(1.0, 0.99 / t);
                 if (pass == 0) {
@@ -674,11 +656,11 @@ EMP_LEVEL_UNROLL
                         mn_z = fmax(mn_z, -z0);
                     }
                 }
-                warp_sum_n(red);
+                L.sum_n(red);
                 const double nrm = sqrt(red[0]);                   // ||s|| == ||z||
                 resx0 = fmax(1.0, sqrt(red[1]));
                 resz0 = fmax(1.0, sqrt(red[2]));
-                const double ts = warp_max(mn_s), tz = warp_max(mn_z);
+                const double ts = L.max(mn_s), tz = L.max(mn_z);
                 const double sh_s = ts >= -1e-8 * fmax(nrm, 1.0) ? 1.0 + ts : 0.0;
                 const double sh_z = tz >= -1e-8 * fmax(nrm, 1.0) ? 1.0 + tz : 0.0;
                 double gs = 0.0;
@@ -693,7 +675,7 @@ EMP_LEVEL_UNROLL
                         gs += sr_ * zr_;
                     }
                 }
-                gap = warp_sum(gs);
+                gap = L.sum(gs);
                 gap_min = gap;
             } else {
                 // step: recompute ds, dz of the corrector pass row by row (cheaper than keeping 28 registers)
@@ -704,8 +686,8 @@ EMP_LEVEL_UNROLL
                 EMP_UNROLL
                 for (int r = 0; r < NR; ++r) {
                     double sr_ = s[r], zr_ = z[r];
-                    const double isr = sm_is[r * 32], rzr = sm_rz[r * 32];
-                    const double bs = (sm_ - sr_ * zr_) - sm_ws[r * 32];
+                    const double isr = sm_is[r * NL], rzr = sm_rz[r * NL];
+                    const double bs = (sm_ - sr_ * zr_) - sm_ws[r * NL];
                     const double tqr = (bs + zr_ * rzr) * isr;
                     const double dzr = tqr + (zr_ * isr) * gdx[r];
                     const double dsr = -rzr - gdx[r];
@@ -721,7 +703,7 @@ EMP_LEVEL_UNROLL
                 for (int c = 0; c < 3; ++c) x[c] += step * dx[c];
                 y[0] += step * dy[0];
                 y[1] += step * dy[1];
-                gap = warp_sum(gs);
+                gap = L.sum(gs);
             }
             ++it;
         }
@@ -747,10 +729,10 @@ EMP_LEVEL_UNROLL
             // Fused all-gather: push the finished plan record into every peer's gather buffer with 16-byte
             // stores over NVLink (peer pointers opened through CUDA IPC); the transfers of finished frames overlap
             // the solves still running on this GPU.  A stream-ordered barrier after the launch makes them visible.
-            __syncwarp();
+            L.sync();
             const double2 *src = reinterpret_cast<const double2 *>(plan);
             const int words2 = p.plan_stride >> 1;
-            for (int w = lane; w < words2; w += 32) {
+            for (int w = lane; w < words2; w += NL) {
                 const double2 vv = src[w];
 #pragma unroll 1
                 for (int r = 0; r < p.n_peers; ++r) {
@@ -760,7 +742,7 @@ EMP_LEVEL_UNROLL
             }
         }
     } else {
-        if (lane < n && n <= EMP_MAX_QP_POINTS) {
+        if (lane < n && n <= NL) {
             double *o = out_x + (size_t)frame * 3 * n;
             o[lane] = x[0];
             o[n + lane] = x[1];
@@ -795,7 +777,7 @@ sl_qp_kernel(const double *__restrict__ scenes, double *__restrict__ plans, doub
         }
         if (frame >= p.batch) break;
         if (p.order != nullptr) frame = p.order[frame];           // heaviest frames first
-        qp_one_frame(frame, lane, scenes, plans, lmin_lmax, lmin_in, lmax_in, start_in, out_x, status_iters, p);
+        qp_one_frame<32>(frame, lane, scenes, plans, lmin_lmax, lmin_in, lmax_in, start_in, out_x, status_iters, p);
         if (ticket == nullptr) return;
         __syncwarp();
     }
@@ -816,6 +798,17 @@ sl_qp_kernel(const double *__restrict__ scenes, double *__restrict__ plans, doub
             }
         }
     }
+}
+
+// General-size path: one CTA of NL threads per frame (33 .. NL stations), static frame -> CTA mapping.
+template <int NL>
+__global__ void __launch_bounds__(NL, 1)
+sl_qp_block_kernel(const double *__restrict__ scenes, double *__restrict__ plans, double *__restrict__ lmin_lmax,
+                   const double *__restrict__ lmin_in, const double *__restrict__ lmax_in,
+                   const double *__restrict__ start_in, double *__restrict__ out_x,
+                   int32_t *__restrict__ status_iters, const QpLaunch p) {
+    const int frame = p.order != nullptr ? p.order[blockIdx.x] : (int)blockIdx.x;
+    qp_one_frame<NL>(frame, (int)threadIdx.x, scenes, plans, lmin_lmax, lmin_in, lmax_in, start_in, out_x, status_iters, p);
 }
 
 // Consumer / flow control of the fused all-gather: one thread per flag spins until it reaches `epoch`, then thread 0
@@ -852,6 +845,17 @@ __device__ unsigned g_qp_tickets[2 * 256];
 
 }  // namespace
 
+template <int NL>
+static cudaError_t launch_block(const double *scenes, double *plans, double *lmin_lmax, const double *lmin_in,
+                                const double *lmax_in, const double *start_in, double *out_x, int32_t *status_iters,
+                                const QpLaunch &p, cudaStream_t st) {
+    const size_t smem = (size_t)(QP_SMEM_ROWS + 2) * NL * sizeof(double);
+    cudaFuncSetAttribute(sl_qp_block_kernel<NL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    sl_qp_block_kernel<NL><<<p.batch, NL, smem, st>>>(scenes, plans, lmin_lmax, lmin_in, lmax_in, start_in, out_x,
+                                                     status_iters, p);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_sl_qp(const double *scenes, double *plans, double *lmin_lmax, const double *lmin_in,
                          const double *lmax_in, const double *start_in, double *out_x, int32_t *status_iters,
                          const QpLaunch &p, cudaStream_t st) {
@@ -859,6 +863,13 @@ cudaError_t launch_sl_qp(const double *scenes, double *plans, double *lmin_lmax,
     static unsigned *ticket_base[64] = {nullptr};
     static int sm_count[64] = {0};
     static const bool persistent = getenv("EMP_QP_STATIC") == nullptr;       // tuning switch: static frame -> warp mapping
+    // stations per frame decide the path: <= 32 one warp per frame; <= 64 / <= 128 one CTA per frame
+    const int n_max = p.mode == QP_MODE_FUSED ? p.n_fused_max : p.n_direct;
+    if (n_max > 32) {
+        if (p.n_peers > 0 || p.epoch != 0ull) return cudaErrorNotSupported;   // the fused gather is a warp-path feature
+        if (n_max <= 64) return launch_block<64>(scenes, plans, lmin_lmax, lmin_in, lmax_in, start_in, out_x, status_iters, p, st);
+        return launch_block<128>(scenes, plans, lmin_lmax, lmin_in, lmax_in, start_in, out_x, status_iters, p, st);
+    }
     const size_t smem = (size_t)QP_WARPS * QP_SMEM_ROWS * 32 * sizeof(double);
     cudaFuncSetAttribute(sl_qp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     const int all = (p.batch + QP_WARPS - 1) / QP_WARPS;

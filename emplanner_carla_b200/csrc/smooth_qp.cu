@@ -18,7 +18,6 @@ namespace emp {
 namespace {
 
 #define EMP_UNROLL _Pragma("unroll")
-constexpr int SM_LEVELS = 5;
 
 __device__ __forceinline__ double frcp(double x) {
     double y;
@@ -44,15 +43,16 @@ struct Fac2 {
     double xl[4], xr[4];        // L^-1 K(i, i-d), L^-1 K(i, i+d), row-major
 };
 
+template <int NL>
 __device__ __forceinline__ bool cr_factor2(double d00, double d10, double d11, const double cl_in[4], const double cr_in[4],
-                                           bool stage, int lane, Fac2 &F) {
+                                           bool stage, int lane, int levels, Lanes<NL> &L, Fac2 &F) {
     double CL[4], CR[4];
     EMP_UNROLL
     for (int k = 0; k < 4; ++k) { CL[k] = cl_in[k]; CR[k] = cr_in[k]; F.xl[k] = 0.0; F.xr[k] = 0.0; }
     F.l10 = 0.0; F.i00 = 1.0; F.i11 = 1.0;
     bool bad = false;
 #pragma unroll 1
-    for (int lev = 0; lev < SM_LEVELS; ++lev) {
+    for (int lev = 0; lev < levels; ++lev) {
         const int d = 1 << lev, msk = 2 * d - 1;
         if ((lane & msk) == d - 1) {
             const double j00 = frsqrt(d00);
@@ -75,12 +75,12 @@ __device__ __forceinline__ bool cr_factor2(double d00, double d10, double d11, c
             EMP_UNROLL
             for (int c = 0; c < 2; ++c) {
                 const double plr = F.xl[r] * F.xr[c] + F.xl[2 + r] * F.xr[2 + c];
-                CL[2 * c + r] = -shfl_up(plr, d);
-                CR[2 * r + c] = -shfl_down(plr, d);
+                CL[2 * c + r] = -L.up(plr, d);
+                CR[2 * r + c] = -L.down(plr, d);
                 if (c <= r) {
                     const double prr = F.xr[r] * F.xr[c] + F.xr[2 + r] * F.xr[2 + c];
                     const double pll = F.xl[r] * F.xl[c] + F.xl[2 + r] * F.xl[2 + c];
-                    const double upd = shfl_up(prr, d) + shfl_down(pll, d);
+                    const double upd = L.up(prr, d) + L.down(pll, d);
                     if (r == 0) d00 -= upd;
                     else if (c == 0) d10 -= upd;
                     else d11 -= upd;
@@ -91,10 +91,12 @@ __device__ __forceinline__ bool cr_factor2(double d00, double d10, double d11, c
     return bad;
 }
 
-__device__ __forceinline__ void cr_solve2(const Fac2 &F, double r0, double r1, int lane, double &y0, double &y1) {
+template <int NL>
+__device__ __forceinline__ void cr_solve2(const Fac2 &F, double r0, double r1, int lane, int levels, Lanes<NL> &L, double &y0,
+                                          double &y1) {
     double t0 = 0.0, t1 = 0.0;
 #pragma unroll 1
-    for (int lev = 0; lev < SM_LEVELS; ++lev) {
+    for (int lev = 0; lev < levels; ++lev) {
         const int d = 1 << lev, msk = 2 * d - 1;
         double ul0 = 0.0, ul1 = 0.0, ur0 = 0.0, ur1 = 0.0;
         if ((lane & msk) == d - 1) {
@@ -103,15 +105,15 @@ __device__ __forceinline__ void cr_solve2(const Fac2 &F, double r0, double r1, i
             ul0 = F.xl[0] * t0 + F.xl[2] * t1; ul1 = F.xl[1] * t0 + F.xl[3] * t1;
             ur0 = F.xr[0] * t0 + F.xr[2] * t1; ur1 = F.xr[1] * t0 + F.xr[3] * t1;
         }
-        r0 -= shfl_up(ur0, d) + shfl_down(ul0, d);
-        r1 -= shfl_up(ur1, d) + shfl_down(ul1, d);
+        r0 -= L.up(ur0, d) + L.down(ul0, d);
+        r1 -= L.up(ur1, d) + L.down(ul1, d);
     }
     y0 = 0.0; y1 = 0.0;
 #pragma unroll 1
-    for (int lev = SM_LEVELS - 1; lev >= 0; --lev) {
+    for (int lev = levels - 1; lev >= 0; --lev) {
         const int d = 1 << lev, msk = 2 * d - 1;
-        const double a0 = shfl_up(y0, d), a1 = shfl_up(y1, d);
-        const double b0 = shfl_down(y0, d), b1 = shfl_down(y1, d);
+        const double a0 = L.up(y0, d), a1 = L.up(y1, d);
+        const double b0 = L.down(y0, d), b1 = L.down(y1, d);
         if ((lane & msk) == d - 1) {
             const double v0 = t0 - ((F.xl[0] * a0 + F.xl[1] * a1) + (F.xr[0] * b0 + F.xr[1] * b1));
             const double v1 = t1 - ((F.xl[2] * a0 + F.xl[3] * a1) + (F.xr[2] * b0 + F.xr[3] * b1));
@@ -121,18 +123,19 @@ __device__ __forceinline__ void cr_solve2(const Fac2 &F, double r0, double r1, i
     }
 }
 
-__global__ void __launch_bounds__(SMO_WARPS * 32)
-smooth_kernel(const double *__restrict__ xy_in, const int32_t *__restrict__ npts, double *__restrict__ out,
-              int32_t *__restrict__ status_iters, const SmoothLaunch p) {
-    __shared__ double scr[SMO_WARPS][3][64];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int line = blockIdx.x * SMO_WARPS + warp;
-    if (line >= p.batch) return;
+// One polyline on NL lanes, two consecutive points per lane: NL = 32 one warp (n <= 64), NL = 64 one CTA (n <= 128).
+// `scr`: this polyline's [3][2 NL] doubles for the heading / curvature stage; `xch`: Lanes<64>'s exchange lines.
+template <int NL>
+__device__ __forceinline__ void
+smooth_one_line(const int line, const int lane, double *__restrict__ scr_base, double *__restrict__ xch,
+                const double *__restrict__ xy_in, const int32_t *__restrict__ npts, double *__restrict__ out,
+                int32_t *__restrict__ status_iters, const SmoothLaunch &p) {
+    Lanes<NL> L(lane, xch);
     const int n = npts ? min(npts[line], p.max_points) : p.max_points;
     const EmpSmoothParams &Q = p.prm;
     int status = 0, it = -1;
     double v[2][2] = {{0.0, 0.0}, {0.0, 0.0}};            // [coordinate][point within lane]
-    if (n < 2 || n > 64) {
+    if (n < 2 || n > 2 * NL) {
         status = EMP_QP_TOO_LARGE;
     } else if (p.heading_only) {
         EMP_UNROLL
@@ -144,6 +147,9 @@ smooth_kernel(const double *__restrict__ xy_in, const int32_t *__restrict__ npts
     } else {
         const int NSTG = (n + 1) >> 1;                     // stages (lanes in use)
         const bool stage = lane < NSTG;
+        // cyclic-reduction levels: log2(NL) eliminate lanes 0 .. NL-2; the last lane is only a stage when the polyline
+        // fills every lane (n = 2 NL - 1, 2 NL) and then takes one more level of its own
+        const int levels = (NL == 32 ? 5 : 6) + (NSTG == NL ? 1 : 0);
         bool on[2];
         double ref[2][2], thr[2] = {Q.x_thre, Q.y_thre};
         double hd[2], ho1[2], ho2[2];                      // pentadiagonal H: diag, (i,i+1), (i,i+2) per point
@@ -167,9 +173,9 @@ smooth_kernel(const double *__restrict__ xy_in, const int32_t *__restrict__ npts
         const int m_rows = 4 * n;
         // H x for one coordinate: needs the neighbours at distance 1 and 2 (previous / next lane)
         auto hmul = [&](const double x[2], double o[2]) {
-            const double pm2 = shfl_up(x[0], 1), pm1 = shfl_up(x[1], 1);       // points 2l-2, 2l-1
-            const double pp2 = shfl_down(x[0], 1), pp3 = shfl_down(x[1], 1);   // points 2l+2, 2l+3
-            const double c_m2 = shfl_up(ho2[0], 1), c_m1a = shfl_up(ho1[1], 1), c_m1b = shfl_up(ho2[1], 1);
+            const double pm2 = L.up(x[0], 1), pm1 = L.up(x[1], 1);       // points 2l-2, 2l-1
+            const double pp2 = L.down(x[0], 1), pp3 = L.down(x[1], 1);   // points 2l+2, 2l+3
+            const double c_m2 = L.up(ho2[0], 1), c_m1a = L.up(ho1[1], 1), c_m1b = L.up(ho2[1], 1);
             const bool has_prev = lane > 0;
             // point 0 of the lane (index 2l): couples 2l-2 (ho2 of 2l-2), 2l-1 (ho1 of 2l-1), 2l+1 (ho1), 2l+2 (ho2)
             o[0] = hd[0] * x[0] + ho1[0] * x[1] + ho2[0] * pp2 + (has_prev ? c_m2 * pm2 + c_m1a * pm1 : 0.0);
@@ -213,10 +219,7 @@ smooth_kernel(const double *__restrict__ xy_in, const int32_t *__restrict__ npts
                         }
                     }
                 }
-                EMP_UNROLL
-                for (int o = 16; o > 0; o >>= 1)
-                    EMP_UNROLL
-                    for (int k = 0; k < 5; ++k) red[k] += shfl_xor(red[k], o);
+                L.sum_n(red);
                 const double resx = sqrt(red[0]), resz = sqrt(red[1]);
                 const double pcost = 0.5 * (red[2] + red[3]);
                 const double dcost = (pcost + red[4]) - gap;
@@ -256,13 +259,13 @@ smooth_kernel(const double *__restrict__ xy_in, const int32_t *__restrict__ npts
                 // couplings: CR = K(lane, lane+1) = [[ho2[0], 0], [ho1[1], ho2[1]]]; CL = K(lane, lane-1) = CR(lane-1)'
                 double CR[4] = {ho2[0], 0.0, ho1[1], ho2[1]};
                 double CL[4];
-                const double p0 = shfl_up(CR[0], 1), p2 = shfl_up(CR[2], 1), p3 = shfl_up(CR[3], 1);
+                const double p0 = L.up(CR[0], 1), p2 = L.up(CR[2], 1), p3 = L.up(CR[3], 1);
                 CL[0] = lane > 0 ? p0 : 0.0; CL[1] = lane > 0 ? p2 : 0.0; CL[2] = 0.0; CL[3] = lane > 0 ? p3 : 0.0;
                 if (!stage) { EMP_UNROLL for (int k = 0; k < 4; ++k) { CR[k] = 0.0; CL[k] = 0.0; } }
                 bad = cr_factor2(stage ? hd[0] + wv[0] : 1.0, stage ? ho1[0] : 0.0, stage ? hd[1] + wv[1] : 1.0, CL, CR,
-                                 stage, lane, F[c]) || bad;
+                                 stage, lane, levels, L, F[c]) || bad;
             }
-            if (__any_sync(EMP_FULL_MASK, bad)) { status = EMP_QP_UNKNOWN_NUMERIC; break; }
+            if (L.any(bad)) { status = EMP_QP_UNKNOWN_NUMERIC; break; }
 
             const double mu = gap / (double)m_rows;
             const int npass = it < 0 ? 1 : 2;
@@ -289,7 +292,7 @@ smooth_kernel(const double *__restrict__ xy_in, const int32_t *__restrict__ npts
                             g[q] = -rx[c][q] - (tq[c][q][0] - tq[c][q][1]);
                         }
                     }
-                    cr_solve2(F[c], stage ? g[0] : 0.0, stage ? g[1] : 0.0, lane, dx[c][0], dx[c][1]);
+                    cr_solve2(F[c], stage ? g[0] : 0.0, stage ? g[1] : 0.0, lane, levels, L, dx[c][0], dx[c][1]);
                 }
                 if (it < 0) break;
                 double dsdz = 0.0, tmax = -1e300;
@@ -308,8 +311,8 @@ smooth_kernel(const double *__restrict__ xy_in, const int32_t *__restrict__ npts
                             }
                             if (pass == 0) ws3[c][q][b] = dsv[c][q][b] * dz[c][q][b];
                         }
-                dsdz = warp_sum(dsdz);
-                const double t = fmax(0.0, warp_max(tmax));
+                dsdz = L.sum(dsdz);
+                const double t = fmax(0.0, L.max(tmax));
                 if (t == 0.0) step = 1.0;
                 else step = pass == 0 ? fmin(1.0, 1.0 / t) : fmin(1.0, 0.99 / t);
                 if (pass == 0) {
@@ -341,14 +344,11 @@ smooth_kernel(const double *__restrict__ xy_in, const int32_t *__restrict__ npts
                         }
                         if (on[q]) red[1] += f * f;
                     }
-                EMP_UNROLL
-                for (int o = 16; o > 0; o >>= 1)
-                    EMP_UNROLL
-                    for (int k = 0; k < 3; ++k) red[k] += shfl_xor(red[k], o);
+                L.sum_n(red);
                 const double nrm = sqrt(red[0]);
                 resx0 = fmax(1.0, sqrt(red[1]));
                 resz0 = fmax(1.0, sqrt(red[2]));
-                const double ts = warp_max(mn_s), tz = warp_max(mn_z);
+                const double ts = L.max(mn_s), tz = L.max(mn_z);
                 const double sh_s = ts >= -1e-8 * fmax(nrm, 1.0) ? 1.0 + ts : 0.0;
                 const double sh_z = tz >= -1e-8 * fmax(nrm, 1.0) ? 1.0 + tz : 0.0;
                 double gs = 0.0;
@@ -363,7 +363,7 @@ smooth_kernel(const double *__restrict__ xy_in, const int32_t *__restrict__ npts
                                 if (sh_z != 0.0) z[c][q][b] += sh_z;
                                 gs += s[c][q][b] * z[c][q][b];
                             }
-                gap = warp_sum(gs);
+                gap = L.sum(gs);
                 gap_min = gap;
             } else {
                 double gs = 0.0;
@@ -380,7 +380,7 @@ smooth_kernel(const double *__restrict__ xy_in, const int32_t *__restrict__ npts
                                 gs += s[c][q][b] * z[c][q][b];
                             }
                     }
-                gap = warp_sum(gs);
+                gap = L.sum(gs);
             }
             ++it;
         }
@@ -388,13 +388,13 @@ smooth_kernel(const double *__restrict__ xy_in, const int32_t *__restrict__ npts
     // ---- outputs: (x, y, theta, kappa) with cal_heading_kappa (:185-228) -------------------------
     double *o = out + (size_t)line * p.max_points * 4;
     if (status != EMP_QP_TOO_LARGE) {
-        double *sx = scr[warp][0], *sy = scr[warp][1], *sth = scr[warp][2];
+        double *sx = scr_base, *sy = scr_base + 2 * NL, *sth = scr_base + 4 * NL;
         EMP_UNROLL
         for (int q = 0; q < 2; ++q) {
             const int i = 2 * lane + q;
             if (i < n) { sx[i] = v[0][q]; sy[i] = v[1][q]; }
         }
-        __syncwarp();
+        L.sync();
         double ddx[2] = {0, 0}, ddy[2] = {0, 0};
         EMP_UNROLL
         for (int q = 0; q < 2; ++q) {
@@ -406,7 +406,7 @@ smooth_kernel(const double *__restrict__ xy_in, const int32_t *__restrict__ npts
                 sth[i] = atan2(ddy[q], ddx[q]);
             }
         }
-        __syncwarp();
+        L.sync();
         EMP_UNROLL
         for (int q = 0; q < 2; ++q) {
             const int i = 2 * lane + q;
@@ -424,6 +424,25 @@ smooth_kernel(const double *__restrict__ xy_in, const int32_t *__restrict__ npts
         status_iters[2 * line] = status;
         status_iters[2 * line + 1] = it < 0 ? 0 : it;
     }
+}
+
+__global__ void __launch_bounds__(SMO_WARPS * 32)
+smooth_kernel(const double *__restrict__ xy_in, const int32_t *__restrict__ npts, double *__restrict__ out,
+              int32_t *__restrict__ status_iters, const SmoothLaunch p) {
+    __shared__ double scr[SMO_WARPS][3 * 64];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int line = blockIdx.x * SMO_WARPS + warp;
+    if (line >= p.batch) return;
+    smooth_one_line<32>(line, lane, scr[warp], nullptr, xy_in, npts, out, status_iters, p);
+}
+
+// polylines of 65 .. 128 points: one CTA of 64 threads per polyline
+__global__ void __launch_bounds__(64)
+smooth_block_kernel(const double *__restrict__ xy_in, const int32_t *__restrict__ npts, double *__restrict__ out,
+                    int32_t *__restrict__ status_iters, const SmoothLaunch p) {
+    __shared__ double scr[3 * 128];
+    __shared__ double xch[2 * 64];
+    smooth_one_line<64>((int)blockIdx.x, (int)threadIdx.x, scr, xch, xy_in, npts, out, status_iters, p);
 }
 
 // cal_heading_kappa (planning_utils.py:185-228) for polylines of any length: one thread per point.  theta_i needs the
@@ -481,6 +500,10 @@ cudaError_t launch_heading_kappa(const double *xy, const int32_t *npts, double *
 
 cudaError_t launch_smooth(const double *xy, const int32_t *npts, double *out, int32_t *status_iters,
                           const SmoothLaunch &p, cudaStream_t st) {
+    if (p.max_points > 64) {                               // general-size path (the kernel reports > 128 as TOO_LARGE)
+        smooth_block_kernel<<<p.batch, 64, 0, st>>>(xy, npts, out, status_iters, p);
+        return cudaGetLastError();
+    }
     const int grid = (p.batch + SMO_WARPS - 1) / SMO_WARPS;
     smooth_kernel<<<grid, SMO_WARPS * 32, 0, st>>>(xy, npts, out, status_iters, p);
     return cudaGetLastError();

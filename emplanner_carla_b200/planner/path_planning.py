@@ -37,8 +37,8 @@ def cal_lmin_lmax(dp_path_s, dp_path_l, obs_s_list, obs_l_list, obs_length, obs_
     dp_s = np.asarray(dp_path_s, dtype=np.float64).reshape(1, -1)
     dp_l = np.asarray(dp_path_l, dtype=np.float64).reshape(1, -1)
     n = dp_s.shape[1]
-    if n > 32:
-        raise NotImplementedError("cal_lmin_lmax on the GPU handles at most 32 path points (got %d)" % n)
+    if n > 128:
+        raise NotImplementedError("cal_lmin_lmax on the GPU handles at most 128 path points (got %d)" % n)
     qp = api.qp_params(obs_length=obs_length, obs_width=obs_width)
     kmax = _runtime.kmax_for(len(obs_s_list))
     pl = _runtime.planner(kmax=kmax)
@@ -59,8 +59,8 @@ def Quadratic_planning(l_min, l_max, plan_start_l, plan_start_dl, plan_start_ddl
     lmin = np.asarray(l_min, dtype=np.float64).reshape(1, -1)
     lmax = np.asarray(l_max, dtype=np.float64).reshape(1, -1)
     n = lmin.shape[1]
-    if n > 32 or n < 2:
-        raise NotImplementedError("Quadratic_planning on the GPU handles 2..32 stations (got %d)" % n)
+    if n > 128 or n < 2:
+        raise NotImplementedError("Quadratic_planning on the GPU handles 2..128 stations (got %d)" % n)
     qp = api.qp_params(dp_sampling_res, w_cost_l, w_cost_dl, w_cost_ddl, w_cost_dddl, w_cost_centre, w_cost_end_l,
                        w_cost_end_dl, w_cost_end_ddl, host_d1, host_d2, host_w)
     pl = _runtime.planner()

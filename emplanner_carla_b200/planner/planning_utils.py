@@ -125,8 +125,8 @@ def smooth_reference_line(local_frenet_path_xy: list,
     Accepts [(x, y), ...] or [(x, y, theta, kappa), ...] (and, like the reference, a first element that is
     only (x, y)); returns [(x_opt, y_opt, theta, kappa), ...]."""
     n = len(local_frenet_path_xy)
-    if n < 2 or n > 64:
-        raise NotImplementedError("smooth_reference_line on the GPU handles 2..64 points (got %d)" % n)
+    if n < 2 or n > 128:
+        raise NotImplementedError("smooth_reference_line on the GPU handles 2..128 points (got %d)" % n)
     xy = _pts(local_frenet_path_xy)
     sp = api.smooth_params(w_cost_smooth, w_cost_length, w_cost_ref, x_thre, y_thre)
     out, status, iters = _runtime.planner().smooth_lines(xy, sp)

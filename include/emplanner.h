@@ -33,7 +33,9 @@ extern "C" {
 #define EMP_NSAMPLE 10           /* samples per lattice edge, path_planning.py:486,559 */
 #define EMP_MAX_ROW 16           /* lattice rows supported by the DP kernel */
 #define EMP_MAX_KMAX 32          /* obstacle slots per scene record */
-#define EMP_MAX_QP_POINTS 32     /* QP stations per frame (one warp lane each) */
+#define EMP_MAX_QP_POINTS 128    /* QP stations per frame: <= 32 one warp per frame (the throughput path), 33..64 and
+                                    65..128 one CTA of 64 / 128 threads per frame (same arithmetic, exchanges through
+                                    shared memory; e.g. sampling_res = 1 gives 46 stations) */
 #define EMP_MAX_PEERS 8          /* GPUs of one NVSwitch box */
 #define EMP_PLAN_SLOTS 4         /* batches in flight through emp_sl_plan_submit */
 #define EMP_ST_KMAX 16           /* dynamic-obstacle slots per S-T scene record */
@@ -52,7 +54,7 @@ extern "C" {
 #define EMP_QP_UNKNOWN_NUMERIC  2     /* 'unknown': factorisation breakdown / non-finite iterate */
 #define EMP_QP_UNKNOWN_DIVERGED 3     /* 'unknown': duality gap grew above diverge_factor x its smallest earlier value */
 #define EMP_QP_CORRIDOR_INDEX   4     /* cal_lmin_lmax would raise IndexError, path_planning.py:265-272 */
-#define EMP_QP_TOO_LARGE        8     /* more than EMP_MAX_QP_POINTS stations, or fewer than 2 */
+#define EMP_QP_TOO_LARGE        8     /* more than EMP_MAX_QP_POINTS (128) stations, or fewer than 2 */
 #define EMP_ST_VALUE_ERROR      0x10  /* the reference raises ValueError (scipy interp1d out of range, empty table) */
 #define EMP_ST_INDEX_ERROR      0x20  /* the reference raises IndexError (S-T profile without NaN terminator, index 16) */
 #define EMP_ST_BAD_PROFILE      0x40  /* S-T profile with fewer than 2 valid points: nothing to smooth */
@@ -240,7 +242,8 @@ int emp_frenet_to_cart_host(EmpPlanner *pl, const double *lines, const double *s
 /* ---- reference-line smoother (K5) ----------------------------------------------------------
  * Replaces planning_utils.smooth_reference_line (:262-361, incl. cvxopt.solvers.qp :353) and
  * cal_heading_kappa (:185-228) for a batch of polylines, one launch.
- * xy: [batch, max_points, 2]; npts[batch] (NULL = max_points), 2 <= n <= 64;
+ * xy: [batch, max_points, 2]; npts[batch] (NULL = max_points), 2 <= n <= 128 (max_points <= 64: one warp per
+ * polyline, the throughput path; 65..128: one CTA of 64 threads per polyline); cal_heading_kappa alone: any length;
  * out: [batch, max_points, 4] = (x_opt, y_opt, theta, kappa); status_iters [batch,2] like emp_qp_dev. */
 int emp_smooth_line_dev(const double *xy, const int32_t *npts, int max_points, int batch, const EmpSmoothParams *p,
                         double *out, int32_t *status_iters, void *stream);

@@ -185,3 +185,38 @@ def test_full_frame_pipeline_dropin(planner):
         sys.path.remove(pkg_dir)
         for k in [k for k in sys.modules if k == "planner" or k.startswith("planner.")]:
             del sys.modules[k]
+
+
+def test_smooth_reference_line_general_sizes(planner):
+    """Polylines longer than the 64 points of the one-warp path (planning_utils.py:262 takes any length): 100 and 128
+    points on the 64-thread CTA path, ragged lengths, against the oracle (reference matrix construction, pinned by
+    golden, + coneqp).  Same tolerances as the 51-point line; 129 points are reported as TOO_LARGE; cal_heading_kappa
+    alone takes any length (the 400-node route)."""
+    from emplanner_carla_b200 import api, scenes
+    from oracle import frenet as ofr
+    xy = scenes.reference_line(128, 2.0)
+    rng = np.random.default_rng(9)
+    B = 6
+    lines = np.stack([xy + rng.normal(0, 0.05, xy.shape) for _ in range(B)])
+    npts = np.array([128, 100, 65, 127, 97, 71], dtype=np.int32)
+    out, status, iters = planner.smooth_lines(lines, api.smooth_params(), npts=npts)
+    for b in range(B):
+        n = int(npts[b])
+        want, info = ofr.smooth_reference_line([tuple(p) for p in lines[b, :n]], diverge_factor=2.0)
+        want = np.array(want)
+        assert status[b] == 0 and info["status"] == "optimal" and iters[b] == info["iterations"]
+        assert np.abs(out[b, :n, :2] - want[:, :2]).max() < 1e-6
+        assert np.abs(out[b, :n, 2] - want[:, 2]).max() < 1e-6 and np.abs(out[b, :n, 3] - want[:, 3]).max() < 1e-6
+    # the one-warp path when the polyline fills every lane (63, 64 points: the last lane is a stage of its own level)
+    out64, st64, it64 = planner.smooth_lines(lines[:, :64], api.smooth_params(), npts=np.array([64, 63, 62, 64, 63, 33], np.int32))
+    for b, n in enumerate([64, 63, 62, 64, 63, 33]):
+        want, info = ofr.smooth_reference_line([tuple(p) for p in lines[b, :n]], diverge_factor=2.0)
+        assert st64[b] == 0 and it64[b] == info["iterations"] and np.abs(out64[b, :n] - np.array(want)).max() < 1e-6
+    big = np.zeros((1, 129, 2))
+    big[0, :, 0] = np.arange(129)
+    _, st, _ = planner.smooth_lines(big, api.smooth_params())
+    assert st[0] == api.QP_TOO_LARGE
+    route = scenes.reference_line(400, 2.0)[None]
+    hk, st, _ = planner.smooth_lines(route, api.smooth_params(heading_only=True))
+    th, kp = ofr.heading_kappa([tuple(p) for p in route[0]])
+    assert st[0] == 0 and np.abs(hk[0, :, 2] - th).max() < 1e-12 and np.abs(hk[0, :, 3] - kp).max() < 1e-12

@@ -314,3 +314,68 @@ def test_nan_obstacle_inside_the_list_is_ignored_like_in_the_reference(planner):
         assert (info["status"] == "optimal") == (int(view.qp_status[b]) == 0)
         m = len(l)
         assert np.sqrt(np.mean((view.qp_l[b, :m] - l) ** 2)) <= 1e-4
+
+
+def test_general_sizes_more_than_32_stations():
+    """Sizes the reference accepts beyond one warp lane per station (path_planning.py:78): sampling_res = 1 on the
+    default lattice gives 91 densified points -> 46 QP stations (one CTA of 64 threads per frame), and a 100-station
+    corridor (128 threads).  Same parity bar as the warp path: status and iteration count equal, RMS(l) <= 1e-4 m,
+    on every frame (same divergence exit on both sides)."""
+    from emplanner_carla_b200 import api, scenes
+    from oracle import sl_dp, sl_qp
+    lat = scenes.Lattice("A_res1", 12, 6, 15, 1.5, 1)
+    B = 48
+    sc = scenes.sl_scenes(B, lat, 91)
+    dp, qp = api.dp_params(**lat.kwargs()), api.qp_params(dp_sampling_res=2)
+    NE = api.max_enriched(dp)
+    assert (NE + 1) // 2 > 32
+    pl = api.HostPlanner(max_batch=B, kmax=8, n_enr_max=NE, max_col=lat.col)
+    try:
+        view, rows = pl.plan(api.pack_scenes(**sc), dp, qp, want_rows=True)
+        o_rows, o_s, o_l, _ = sl_dp.dp_batch(sc["obs_s"], sc["obs_l"], sc["nobs"], sc["s0"], sc["l0"], sc["dl0"],
+                                             sc["ddl0"], **lat.kwargs())
+        assert np.array_equal(rows, o_rows)
+        worst, n_unknown = 0.0, 0
+        for b in range(B):
+            K = int(sc["nobs"][b])
+            es, el = sl_dp.enrich(o_s[b], o_l[b], sc["s0"][b], sc["l0"][b], sc["dl0"][b], sc["ddl0"][b], lat.sampling_res)
+            assert int(view.n_enr[b]) == len(es) and 88 <= len(es) <= 91     # Q10: int(end_s - start_s) per segment
+            try:
+                lmin, lmax = sl_qp.corridor(es[::2], el[::2], sc["obs_s"][b, :K], sc["obs_l"][b, :K], 5, 5)
+            except IndexError:
+                assert int(view.qp_status[b]) == api.QP_CORRIDOR_INDEX
+                continue
+            l, _, _, info = sl_qp.quadratic_planning(lmin, lmax, sc["l0"][b], sc["dl0"][b], sc["ddl0"][b], diverge_factor=2.0)
+            m = len(l)
+            assert int(view.n_qp[b]) == m and 44 <= m <= 46
+            assert (info["status"] == "optimal") == (int(view.qp_status[b]) == 0), b
+            assert int(view.qp_iters[b]) == info["iterations"], b
+            n_unknown += info["status"] != "optimal"
+            worst = max(worst, float(np.sqrt(np.mean((view.qp_l[b, :m] - l) ** 2))))
+        print("46-station QP (block path, 64 threads): worst RMS %.2e, unknown frames %d" % (worst, n_unknown))
+        assert worst <= 1e-4
+        # direct entry point, 100 stations (128 threads per frame), hand-made corridors
+        rng = np.random.default_rng(5)
+        n, Bq = 100, 16
+        lmin = np.full((Bq, n), -10.0)
+        lmax = np.full((Bq, n), 10.0)
+        for b in range(Bq):
+            for _ in range(3):
+                a = int(rng.integers(10, 80))
+                if rng.random() < 0.5:
+                    lmax[b, a:a + 6] = rng.uniform(-1.0, 2.0)
+                else:
+                    lmin[b, a:a + 6] = rng.uniform(-2.0, 1.0)
+        start = np.stack([rng.uniform(-0.3, 0.3, Bq), rng.uniform(-0.02, 0.02, Bq), rng.uniform(-0.01, 0.01, Bq)], axis=1)
+        x, st, it = pl.qp(lmin, lmax, start, qp)
+        worst = 0.0
+        for b in range(Bq):
+            l, dl, ddl, info = sl_qp.quadratic_planning(lmin[b], lmax[b], *start[b], diverge_factor=2.0)
+            assert (info["status"] == "optimal") == (st[b] == 0) and it[b] == info["iterations"], b
+            worst = max(worst, float(np.sqrt(np.mean((x[b, 0] - l) ** 2))), float(np.abs(x[b, 1] - dl).max()))
+        print("100-station QP (block path, 128 threads): worst deviation %.2e" % worst)
+        assert worst <= 1e-4
+        xs, sts, _ = pl.qp(np.full((2, 129), -10.0), np.full((2, 129), 10.0), np.zeros((2, 3)), qp)
+        assert np.all(sts == api.QP_TOO_LARGE)
+    finally:
+        pl.close()
