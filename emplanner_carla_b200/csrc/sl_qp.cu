@@ -755,22 +755,27 @@ EMP_LEVEL_UNROLL
     }
 }
 
-// Persistent launch: grid = resident CTAs (EMP_QP_MINBLOCKS per SM), every warp pulls the next frame from a ticket
-// counter until the batch is exhausted.  Solve times differ by 2x between frames (6 .. 13 interior-point iterations),
-// and 4096 frames are 3.46 waves of the 1184 resident warps: with a static frame -> warp mapping the launch ends with a
-// fourth wave that is less than half full; with the queue it ends within one solve of the average.
-// ticket[0] = next frame, ticket[1] = warps that have left the loop; the last one to leave re-arms both for the next
-// launch that is handed this slot (launch_sl_qp rotates slots, so concurrent launches never share one).
+// Frame -> warp mapping.  Default: static, warp w of the grid solves frame order[w] (heaviest frames first when the
+// emp_sl_order_dev schedule is given), one frame per warp; CTAs retire one by one, so the next step's DP kernel (another
+// stream) moves in while this launch drains - worth 2 % of the pipelined step over the queue below.
+// Queue (`queue` != 0, EMP_QP_QUEUE=1): grid = resident CTAs (EMP_QP_MINBLOCKS per SM), every warp pulls the next frame
+// from a ticket counter until the batch is exhausted.  Solve times differ by 2x between frames (6 .. 13 interior-point
+// iterations) and 4096 frames are 3.46 waves of the 1184 resident warps; the queue ends the launch within one solve of
+// the average (1-3 % faster launched alone), but its CTAs hold every register of the SM until the very end.
+// ticket[0] = next frame, ticket[1] = warps that are done; the last one re-arms both for the next launch that is handed
+// this slot (launch_sl_qp rotates slots, so concurrent launches never share one) and, in the fused all-gather,
+// publishes the launch's epoch.
 __global__ void __launch_bounds__(QP_WARPS * 32, EMP_QP_MINBLOCKS)
 sl_qp_kernel(const double *__restrict__ scenes, double *__restrict__ plans, double *__restrict__ lmin_lmax,
              const double *__restrict__ lmin_in, const double *__restrict__ lmax_in,
              const double *__restrict__ start_in, double *__restrict__ out_x,
-             int32_t *__restrict__ status_iters, unsigned *__restrict__ ticket, const QpLaunch p) {
+             int32_t *__restrict__ status_iters, unsigned *__restrict__ ticket, const int queue,
+             const QpLaunch p) {
     const int lane = threadIdx.x & 31;
 #pragma unroll 1
     for (;;) {
-        int frame = blockIdx.x * QP_WARPS + (threadIdx.x >> 5);    // static mapping when no queue is given
-        if (ticket != nullptr) {
+        int frame = blockIdx.x * QP_WARPS + (threadIdx.x >> 5);    // static mapping
+        if (queue) {
             unsigned t = 0;
             if (lane == 0) t = atomicAdd(ticket, 1u);
             frame = (int)__shfl_sync(EMP_FULL_MASK, t, 0);
@@ -778,8 +783,8 @@ sl_qp_kernel(const double *__restrict__ scenes, double *__restrict__ plans, doub
         if (frame >= p.batch) break;
         if (p.order != nullptr) frame = p.order[frame];           // heaviest frames first
         qp_one_frame<32>(frame, lane, scenes, plans, lmin_lmax, lmin_in, lmax_in, start_in, out_x, status_iters, p);
-        if (ticket == nullptr) return;
         __syncwarp();
+        if (!queue) break;
     }
     if (ticket == nullptr) return;
     if (lane == 0) {
@@ -862,7 +867,7 @@ cudaError_t launch_sl_qp(const double *scenes, double *plans, double *lmin_lmax,
     static std::atomic<unsigned> next_slot{0};
     static unsigned *ticket_base[64] = {nullptr};
     static int sm_count[64] = {0};
-    static const bool persistent = getenv("EMP_QP_STATIC") == nullptr;       // tuning switch: static frame -> warp mapping
+    static const bool use_queue = getenv("EMP_QP_QUEUE") != nullptr;         // tuning switch: persistent CTAs + ticket queue
     // stations per frame decide the path: <= 32 one warp per frame; <= 64 / <= 128 one CTA per frame
     const int n_max = p.mode == QP_MODE_FUSED ? p.n_fused_max : p.n_direct;
     if (n_max > 32) {
@@ -876,8 +881,8 @@ cudaError_t launch_sl_qp(const double *scenes, double *plans, double *lmin_lmax,
     int dev = 0;
     cudaGetDevice(&dev);
     unsigned *ticket = nullptr;
-    int grid = all;
-    if (persistent && dev >= 0 && dev < 64) {
+    int grid = all, queue = 0;
+    if ((use_queue || p.epoch != 0ull) && dev >= 0 && dev < 64) {
         if (ticket_base[dev] == nullptr) {
             void *sym = nullptr;
             if (cudaGetSymbolAddress(&sym, g_qp_tickets) != cudaSuccess) return cudaGetLastError();
@@ -885,14 +890,16 @@ cudaError_t launch_sl_qp(const double *scenes, double *plans, double *lmin_lmax,
             ticket_base[dev] = static_cast<unsigned *>(sym);
         }
         const int resident = sm_count[dev] * EMP_QP_MINBLOCKS;
-        if (all > resident || p.epoch != 0ull) {                   // more frames than resident warps: queue them
-            grid = all < resident ? all : resident;                // (the arrival flags need the "last warp" count too)
-            ticket = ticket_base[dev] + 2 * (next_slot.fetch_add(1) % 256u);
+        if (use_queue && all > resident) {                         // more frames than resident warps: queue them
+            grid = resident;
+            queue = 1;
         }
+        if (queue || p.epoch != 0ull)                              // the arrival flags need the "last warp" count
+            ticket = ticket_base[dev] + 2 * (next_slot.fetch_add(1) % 256u);
     }
     if (p.epoch != 0ull && ticket == nullptr) return cudaErrorNotSupported;
     sl_qp_kernel<<<grid, QP_WARPS * 32, smem, st>>>(scenes, plans, lmin_lmax, lmin_in, lmax_in, start_in, out_x,
-                                                 status_iters, ticket, p);
+                                                 status_iters, ticket, queue, p);
     return cudaGetLastError();
 }
 
