@@ -182,6 +182,15 @@ def cpu_port_throughput(lat_name, config_id, frames, cores, total):
     return done / wall, done, wall, sum(r[1] for r in res) / max(sum(r[2] for r in res), 1e-9)
 
 
+_T0 = time.perf_counter()
+
+
+def trace(msg):
+    """Progress marks on stderr (EMP_BENCH_TRACE=1): which phase a multi-rank run is in."""
+    if os.environ.get("EMP_BENCH_TRACE"):
+        print("[bench %6.1fs rank %s] %s" % (time.perf_counter() - _T0, os.environ.get("RANK", "0"), msg), file=sys.stderr, flush=True)
+
+
 def host_cores():
     try:
         return len(os.sched_getaffinity(0))
@@ -259,6 +268,10 @@ class SlWorkload:
         self.flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev) if flush else None
         self.main = torch.cuda.current_stream()
         self.streams = [torch.cuda.Stream(device=dev) for _ in range(P)] if P > 1 else [self.main]
+        # N > 1, fused gather: the consumer side (wait for every rank's shard, hand the buffer back) runs on its own
+        # stream per slot, so rank skew never stalls the stream that launches the next step's kernels
+        self.cons = [torch.cuda.Stream(device=dev) for _ in range(P)] if self.p2p else None
+        self.done_ev = [None] * nb
         self.launches_per_step = 3 + (1 if self.p2p else 0) + (1 if self.p2p else 0)   # order, DP, QP (+ credit wait, consume)
 
     def step(self, k, ev=None):
@@ -270,6 +283,8 @@ class SlWorkload:
             self.flush.fill_(k & 0xFF)
         if ev:
             ev[0].record(st)
+        if self.done_ev[b] is not None:
+            st.wait_event(self.done_ev[b])                             # this rank's consumer is done with buffer set b
         api.order_device(sc, od)
         if ev:
             ev[1].record(st)
@@ -283,8 +298,18 @@ class SlWorkload:
         if ev:
             ev[3].record(st)
         if self.world > 1:
-            if self.p2p:
-                gb.consume()                                           # wait for every shard, hand the buffer back
+            if self.p2p and ev is None:
+                torch = self.torch
+                ready = torch.cuda.Event()
+                ready.record(st)
+                cs = self.cons[k % self.P]
+                with torch.cuda.stream(cs):
+                    cs.wait_event(ready)
+                    gb.consume()                                       # wait for every shard, hand the buffer back
+                    self.done_ev[b] = torch.cuda.Event()
+                    self.done_ev[b].record(cs)
+            elif self.p2p:
+                gb.consume()                                           # serial pass: on the launching stream, timed
             else:
                 gb.all_gather()                                        # one in-place NCCL all-gather of plan records
         if ev:
@@ -311,6 +336,9 @@ class SlWorkload:
         if self.P > 1:
             for s in self.streams:
                 self.main.wait_stream(s)
+        if self.cons is not None:
+            for s in self.cons:
+                self.main.wait_stream(s)                               # the step is done when the gathered batch is there
         e1.record(self.main)
         self.sync()
         return e0.elapsed_time(e1)
@@ -498,11 +526,14 @@ def extra_config4(torch, dist, api, lat, rank, world, dev, K, min_seconds):
             return e0.elapsed_time(e1), buf
 
         region()
-        times, total = [], 0.0
-        while len(times) < 3 or (total < min_seconds * 1e3 and len(times) < 100):
+        cal = torch.tensor([region()[0]], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(cal, op=dist.ReduceOp.MAX)                 # every rank must run the same number of regions
+        n_regions = int(min(100, max(3, math.ceil(min_seconds * 1e3 / max(float(cal.item()), 1e-3)))))
+        times = []
+        for _ in range(n_regions):
             ms, buf = region()
             times.append(ms)
-            total += ms
         tt = torch.tensor(times, dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
@@ -567,14 +598,19 @@ def main():
 
     B, K = args.batch, args.steps
     P = max(1, min(args.pipeline, api.PLAN_SLOTS))
+    trace("process group up")
     wl = SlWorkload(torch, dist, api, sharding, lat, config_id, B, rank, world, dev, args.gather, P, args.flush)
 
+    trace("workload buffers ready (%d buffer sets)" % wl.NB)
     sampler = ClockSampler(local)
     sampler.start()
     times = wl.timed(K, args.warmup, args.min_seconds)                 # the timed regions of `value`
     clocks = sampler.stop()
+    trace("timed regions done (%d)" % len(times))
     seg = wl.serial(K)                                                 # per-kernel events, one step at a time
+    trace("serial pass done")
     gather_ok = wl.verify_gather()
+    trace("gather verified: %s" % gather_ok)
     med = float(np.median(times))
     value = B * world * K / (med * 1e-3)
     t_order, t_dp, t_qp, t_coll, t_ser = seg
@@ -584,6 +620,7 @@ def main():
     else:
         e_times, h2d, d2h, e_api = e2e_multi(torch, wl, K, args.warmup, args.min_seconds)
         gather_ok = gather_ok and wl.verify_gather()
+    trace("e2e done")
     e_med = float(np.median(e_times))
     e2e_val = B * world * K / e_med
 
@@ -591,7 +628,9 @@ def main():
     if not args.no_extras:
         extra["config2"] = extra_config2(torch, dist, api, sharding, lat, rank, world, dev, args.gather, P, K,
                                          args.min_seconds / 2)
+        trace("extra config2 done")
         extra["config4"] = extra_config4(torch, dist, api, lat, rank, world, dev, max(2, K // 4), args.min_seconds / 2)
+        trace("extra config4 done")
 
     if rank != 0:
         wl.close()

@@ -7,7 +7,8 @@ Tolerances (stated per test):
          golden frames of lattices A / B / C): <= 1e-10 m on A, <= 1e-9 m on B/C (observed 2.9e-12 /
          2.8e-11 / 3.8e-11, the reference's own 6x6-inverse noise), zero row or length flips.
   QP   : per-frame RMS(l_gpu - l_oracle) <= 1e-4 m (north_star) on EVERY frame, optimal or not; status agreement
-         100 %; iteration counts equal on >= 99 %.  Observed numbers are written to gpurun_out/parity/.
+         100 %; iteration counts equal on every frame.  Observed numbers (profiles/parity_r2.json): worst RMS 2.2e-10 m on
+         converging frames, 9.0e-8 m on 'unknown' frames.
 """
 import numpy as np
 import pytest
@@ -138,8 +139,8 @@ def test_plan_matches_golden_qp_on_every_frame(planner, tag):
     assert r1["status_disagree"] == 0 and r2["status_disagree"] == 0
     assert r1["worst_rms_optimal"] <= 1e-4 and r1["worst_rms_unknown"] <= 1e-4
     assert r2["worst_rms_optimal"] <= 1e-4
-    assert r1["iter_mismatch_optimal"] + r1["iter_mismatch_unknown"] <= max(1, r1["frames"] // 100)
-    assert r2["iter_mismatch_optimal"] <= max(1, r2["frames"] // 100)
+    assert r1["iter_mismatch_optimal"] + r1["iter_mismatch_unknown"] == 0      # observed: 0 of 512 / 128 / 1024 frames
+    assert r2["iter_mismatch_optimal"] == 0
     # frames that converge are untouched by the divergence exit: same bits out of the kernel either way
     opt = ok & (g["qp_optimal"] == 1)
     assert np.array_equal(view.qp_l[opt], view0.qp_l[opt]) and np.array_equal(view.qp_iters[opt], view0.qp_iters[opt])
