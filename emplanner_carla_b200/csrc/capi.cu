@@ -45,6 +45,8 @@ int make_dp_launch(emp::DpLaunch &L, const EmpDpParams *p, int kmax, int batch, 
     if (p->col < 1 || p->col > 4096) return fail(-2, "col must be in [1, 4096]");
     if (kmax < 0 || kmax > EMP_MAX_KMAX || (kmax & 1)) return fail(-2, "kmax must be even and in [0, 32]");
     if (!(p->sample_s > 0) || !(p->sampling_res > 0)) return fail(-2, "sample_s and sampling_res must be > 0");
+    // the branch and bound of K1 uses "cost without the collision term" as a lower bound: needs w_collision >= 0
+    if (!(p->w_collision >= 0)) return fail(-2, "w_collision_cost must be >= 0");
     if (batch < 0 || n_enr_max < 2) return fail(-2, "bad batch / n_enr_max");
     L.res = p->sampling_res;
     L.w_col = p->w_collision;
@@ -333,6 +335,8 @@ int emp_st_dp_dev(const double *scenes, int kmax, int batch, const EmpStParams *
     if (!p) return fail(-1, "EmpStParams is NULL");
     if (kmax < 0 || kmax > EMP_ST_KMAX || (kmax & 1)) return fail(-2, "kmax must be even and in [0, 16]");
     if (batch < 0) return fail(-2, "bad batch");
+    // w^(1.5-d) is evaluated as exp((1.5-d) ln w), and the pruning bound needs a non-negative obstacle term
+    if (!(p->w_obs > 0)) return fail(-2, "w_cost_obs must be > 0");
     if (batch == 0) return 0;
     if (!scenes || !out) return fail(-1, "scenes/out is NULL");
     emp::StLaunch L{*p, batch, kmax, 2 + 4 * kmax};

@@ -404,6 +404,7 @@ speed_qp_kernel(const double *__restrict__ start, const double *__restrict__ st_
             if (!isfinite((gap + resx) + resz)) { status = EMP_QP_UNKNOWN_NUMERIC; break; }
             if (it > 0 && Q.diverge_factor > 0.0 && gap > Q.diverge_factor * gap_min) {
                 status = EMP_QP_UNKNOWN_DIVERGED;                      // the step that blew the gap up is discarded
+                __syncwarp();                                          // every lane is done reading W.x (residuals above)
                 EMP_UNROLL
                 for (int t = 0; t < 2; ++t)
                     if (vo[t]) W.x[lane + 32 * t] = xp[t];

@@ -47,6 +47,13 @@ def test_argument_errors_are_reported_not_crashed():
     assert rc < 0 and b"row" in lib.emp_last_error()
     with pytest.raises(_lib.EmpError):
         _lib.check(rc)
+    # weights the exact branch and bound cannot take are argument errors, not silently different answers
+    d = _lib.dp_params(w_collision_cost=-1.0)
+    assert lib.emp_sl_dp_dev(None, 8, 4, ctypes.byref(d), 49, None, None, None, None) < 0
+    assert b"w_collision" in lib.emp_last_error()
+    st = _lib.st_params(w_cost_obs=0.0)
+    assert lib.emp_st_dp_dev(None, 8, 4, ctypes.byref(st), None, None, None, None, None) < 0
+    assert b"w_cost_obs" in lib.emp_last_error()
 
 
 def test_pack_scenes_layout_and_scene_prefix_property():
