@@ -789,7 +789,11 @@ sl_qp_kernel(const double *__restrict__ scenes, double *__restrict__ plans, doub
     if (ticket == nullptr) return;
     if (lane == 0) {
         const unsigned total = gridDim.x * QP_WARPS;
-        if (p.epoch != 0ull) __threadfence_system();             // this warp's peer stores before its arrival below
+        // This warp's peer stores before its arrival below.  A device-scope fence is enough here: the arrival counter
+        // synchronises the warps of this GPU, and the last warp's system-scope fence + release below is cumulative over
+        // everything it has observed (PTX memory model: causality order composes across scopes) - the same shape as
+        // "stores, __syncthreads(), one thread fences at system scope and signals".
+        if (p.epoch != 0ull) __threadfence();
         if (atomicAdd(ticket + 1, 1u) == total - 1) {             // every other warp is past its last ticket read
             ticket[0] = 0u;
             ticket[1] = 0u;
