@@ -363,9 +363,11 @@ int emp_misc_host(EmpPlanner *pl, int op, const double *in, int n, int batch, co
 /* ---- fused planning step + all-gather over NVLink peer memory --------------------------------
  * Same as emp_sl_plan_dev, and every finished plan record is also stored into `peer_slices[r]` (r < n_peers):
  * device pointers into the OTHER GPUs' gather buffers at this rank's slice, obtained with emp_ipc_open.
- * The stores overlap the solves still running; a stream-ordered barrier across ranks (e.g. a 1-element NCCL
- * all-reduce) after the call makes the gathered batch visible everywhere.  Replaces the north_star's
- * "single NCCL all-gather of the solved paths" with P2P writes from inside the QP kernel. */
+ * The stores overlap the solves still running.  This entry point carries no completion signal: the gathered batch
+ * is only guaranteed visible on a peer after the caller's own cross-rank barrier that follows the call in stream
+ * order.  The product path (sharding.PeerGatherBuffer, bench.py) uses emp_sl_qp_gather_dev below instead, whose
+ * arrival flags make that barrier unnecessary; this one is kept for callers that already synchronise each cycle.
+ * Replaces the north_star's "single NCCL all-gather of the solved paths" with P2P writes from inside the QP kernel. */
 int emp_sl_plan_p2p_dev(const double *scenes, int kmax, int batch, const EmpDpParams *dp, const EmpQpParams *qp,
                         int n_enr_max, double *plans, int32_t *rows, int n_peers, double *const *peer_slices,
                         int32_t *order_ws, void *stream);
