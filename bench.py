@@ -450,23 +450,77 @@ def e2e_single(api, wl, K, warmup, min_seconds, local):
     return times, int(recs[0].nbytes), int(outs[0].nbytes), api_name
 
 
-def e2e_multi(torch, wl, K, warmup, min_seconds):
+def numa_bind(torch, dev):
+    """Run this rank on the CPUs of the NUMA node its GPU hangs off, so page-locked buffers allocated afterwards are
+    local to the GPU's PCIe root (first touch).  Returns a description, or None when sysfs does not say."""
+    try:
+        bus = torch.cuda.get_device_properties(dev).pci_bus_id
+        dom = torch.cuda.get_device_properties(dev).pci_domain_id
+        devid = torch.cuda.get_device_properties(dev).pci_device_id
+        path = "/sys/bus/pci/devices/%04x:%02x:%02x.0/numa_node" % (dom, bus, devid)
+        node = int(open(path).read().strip())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open("/sys/devices/system/node/node%d/cpulist" % node).read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return {"node": node, "cpus": len(cpus)}
+    except Exception:
+        return None
+
+
+def e2e_multi(torch, wl, K, warmup, min_seconds, copy_streams=None):
     """N > 1: pinned host scenes -> H2D -> schedule/DP/QP with the fused gather -> consume -> D2H of the rank's own
-    shard of plan records, every step, on the P slot streams; wall clock between barriers, max over ranks."""
+    shard of plan records, every step; wall clock between barriers, max over ranks.
+    copy_streams: the copies run on a copy-in and a copy-out stream per slot, ordered against the slot's kernels with
+    events, so a slow PCIe copy never sits between two steps' kernels on the launching stream."""
+    if copy_streams is None:
+        copy_streams = os.environ.get("EMP_BENCH_COPY_STREAMS", "1") != "0"
     B, P = wl.B, wl.P
     pin_in = [torch.from_numpy(wl.rec_host).clone().pin_memory() for _ in range(P)]
     pin_out = [torch.empty((B, wl.stride), dtype=torch.float64).pin_memory() for _ in range(P)]
     state = {"k": 10 * wl.NB}                                          # keep buffer set / stream pairing (k % NB, k % P)
+    cin = [torch.cuda.Stream(device=wl.dev) for _ in range(P)] if copy_streams else None
+    cout = [torch.cuda.Stream(device=wl.dev) for _ in range(P)] if copy_streams else None
+    solved = [None] * wl.NB                                            # buffer set b: its kernels are done
+    copied = [None] * wl.NB                                            # buffer set b: its shard is on the host
 
     def steps(n):
         for _ in range(n):
             k = state["k"]
             state["k"] += 1
             b, s = k % wl.NB, k % P
-            with torch.cuda.stream(wl.streams[s]):
+            st = wl.streams[s]
+            if not copy_streams:
+                with torch.cuda.stream(st):
+                    wl.scenes[b].copy_(pin_in[s], non_blocking=True)
+                    wl.step(k)
+                    pin_out[s].copy_(wl.gbufs[b].mine, non_blocking=True)
+                continue
+            with torch.cuda.stream(cin[s]):
+                if solved[b] is not None:
+                    cin[s].wait_event(solved[b])                       # the last kernels that read scenes[b]
                 wl.scenes[b].copy_(pin_in[s], non_blocking=True)
+                here = torch.cuda.Event()
+                here.record(cin[s])
+            with torch.cuda.stream(st):
+                st.wait_event(here)
+                if copied[b] is not None:
+                    st.wait_event(copied[b])                           # the shard of set b's last use has left the GPU
                 wl.step(k)
+                solved[b] = torch.cuda.Event()
+                solved[b].record(st)
+            with torch.cuda.stream(cout[s]):
+                cout[s].wait_event(solved[b])
                 pin_out[s].copy_(wl.gbufs[b].mine, non_blocking=True)
+                copied[b] = torch.cuda.Event()
+                copied[b].record(cout[s])
+        state["enqueued"] = time.perf_counter()
         torch.cuda.synchronize()
 
     steps(max(warmup, 3))
@@ -476,16 +530,20 @@ def e2e_multi(torch, wl, K, warmup, min_seconds):
     steps(K)
     cal = wl.max_over_ranks([time.perf_counter() - t0])[0]
     n_regions = int(min(400, max(3, math.ceil(min_seconds / max(cal, 1e-6)))))
+    enq = []
     for _ in range(n_regions):
         wl.sync()
         t0 = time.perf_counter()
         steps(K)
         times.append(time.perf_counter() - t0)
+        enq.append(state["enqueued"] - t0)
     times = wl.max_over_ranks(times)
+    e2e_multi.host_enqueue_s = float(np.median(wl.max_over_ranks(enq)))   # host time to enqueue a region, slowest rank
     return times, int(pin_in[0].nbytes) * wl.world, int(pin_out[0].nbytes) * wl.world, (
         "torch pinned host tensors -> api.order_device / dp_device / sharding.PeerGatherBuffer.plan_qp + consume "
         "(or qp_device + NCCL all-gather) -> D2H of the rank's own shard; every GPU ends each step holding the gathered "
-        "batch, each rank returns its shard to its host; bytes are summed over ranks")
+        "batch, each rank returns its shard to its host; bytes are summed over ranks" +
+        ("; copies on a copy-in / copy-out stream per slot" if copy_streams else ""))
 
 
 def extra_config2(torch, dist, api, sharding, lat, rank, world, dev, gather, P, K, min_seconds):
@@ -611,6 +669,7 @@ def main():
         raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    numa = numa_bind(torch, dev) if world > 1 else None              # before any page-locked allocation
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
@@ -751,6 +810,8 @@ def main():
     }
     if world > 1:
         line["gather_verified"] = gather_ok
+        line["e2e"]["host_enqueue_ms_per_step"] = e2e_multi.host_enqueue_s / K * 1e3
+        line["e2e"]["numa_bound"] = numa
     if extra:
         line["extra"] = extra
     if cpu:
