@@ -1,7 +1,11 @@
 #!/usr/bin/env python
 """Attribute ncu stall samples / executed instructions to CUDA source lines.
 usage: ncu_lines.py report.ncu-rep <kernel-regex> <cubin> <mangled-substring> [top]
-The cubin must be the one the report was taken with (cuobjdump -xelf all libemplanner.so)."""
+The cubin must be the one the report was taken with (cuobjdump -xelf all libemplanner.so).
+Caveat: nvdisasm reports one line per instruction; code inlined from a lambda or a helper is attributed to whatever
+line the compiler kept (often the lambda's first statement or the call site), so a single line can collect a whole
+inlined loop.  Cross-check a surprising line against the per-instruction counts of `ncu --page source --csv`
+(e.g. the integer division `e / R` in sl_dp.cu's exact() shows 12.9 % here and 1.5 % by its SASS sequence)."""
 import csv, io, re, subprocess, sys
 from collections import defaultdict
 rep, kre, cubin, sym = sys.argv[1:5]
