@@ -82,6 +82,7 @@ int make_dp_launch(emp::DpLaunch &L, const EmpDpParams *p, int kmax, int batch, 
     L.w_off_dlon = w;   w += align_up((kmax > 0 ? kmax : 1) * (EMP_NSAMPLE + 1) * 8, 16);
     L.w_off_k0 = w;     w += EMP_MAX_ROW * 4;
     L.w_off_wl = w;     w += align_up(RR * 2, 16);
+    L.w_off_pv = w;     w += align_up(emp::DP_PAIR_CAND * EMP_NSAMPLE * 8 + emp::DP_PAIR_CAND * 2, 16);
     L.warp_bytes = w;
     L.smem_bytes = (unsigned)(off + emp::DP_WARPS * w);
     if (L.smem_bytes > 227u * 1024u) return fail(-3, "lattice too large for shared memory (row*col)");

@@ -18,12 +18,14 @@ namespace emp {
 constexpr int DP_WARPS = EMP_DP_WARPS;   // frames (warps) per CTA in the DP kernel
 constexpr int QP_WARPS = EMP_QP_WARPS;   // frames (warps) per CTA in the QP kernel
 
+constexpr int DP_PAIR_CAND = 16;   // candidates per chunk of the DP kernel's (candidate, sample) pair evaluation (>= EMP_MAX_ROW)
+
 struct DpLaunch {
     double res, w_col, w0, w1, w2, w_ref, sample_s, sample_l;
     int R, C, kmax, n_enr_max, scene_stride, plan_stride, batch;
     // shared-memory carve-up (bytes)
     int off_slab, off_f0, off_nl, off_refc, off_ltab, off_warp, warp_bytes;
-    int w_off_cand, w_off_cost, w_off_rows, w_off_offs, w_off_parent, w_off_sj, w_off_dlon, w_off_k0, w_off_wl;
+    int w_off_cand, w_off_cost, w_off_rows, w_off_offs, w_off_parent, w_off_sj, w_off_dlon, w_off_k0, w_off_wl, w_off_pv;
     unsigned smem_bytes;
     const int32_t *order;     // optional [batch]: work slot -> frame (launch_sl_order); NULL = natural order
 };
