@@ -642,7 +642,7 @@ def main():
     ap.add_argument("--flush", action="store_true",
                     help="flush L2 with a 256 MiB write before every step instead of rotating over buffer sets")
     ap.add_argument("--min-seconds", type=float, default=0.25, help="timed work to accumulate by repeating the K-step region")
-    ap.add_argument("--pipeline", type=int, default=2,
+    ap.add_argument("--pipeline", type=int, default=4,
                     help="batches in flight: step k+1's kernels (and copies) overlap step k's on another stream; "
                          "1 = strictly serial steps")
     ap.add_argument("--gather", default="p2p", choices=["p2p", "nccl"],
