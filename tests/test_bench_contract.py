@@ -52,3 +52,30 @@ def test_product_arm_line_on_gpu():
     assert set(d["kernels_ms"]) == {"sl_order_kernel", "sl_dp_kernel", "sl_qp_kernel", "collective"}
     assert set(d["clocks"]) >= {"sm_mhz", "sm_max_mhz", "reasons"}
     assert d["pipeline"]["batches_in_flight"] >= 1 and d["pipeline"]["value_serial_steps"] > 0
+
+
+def test_bench_defaults_and_host_helpers():
+    """Defaults the driver relies on (no flags: one GPU, minutes) and the host-side helpers that must never raise."""
+    sys.path.insert(0, ROOT)
+    import bench
+    from emplanner_carla_b200 import api
+
+    class _Props:                      # a device whose sysfs entry does not exist: numa_bind reports nothing, changes nothing
+        pci_bus_id, pci_domain_id, pci_device_id = 0xfe, 0xffff, 0x1f
+
+    class _Torch:
+        class cuda:
+            @staticmethod
+            def get_device_properties(dev):
+                return _Props()
+
+    before = os.sched_getaffinity(0)
+    assert bench.numa_bind(_Torch, 0) is None and os.sched_getaffinity(0) == before
+    src = open(os.path.join(ROOT, "bench.py")).read()
+    assert 'add_argument("--pipeline", type=int, default=4' in src and api.PLAN_SLOTS >= 4
+    assert 'add_argument("--gpus", type=int, default=1)' in src and 'add_argument("--warmup", type=int, default=3)' in src
+    h = bench.source_hashes()
+    assert set(h) == {"sl_dp.cu", "sl_qp.cu"}
+    facts, path = bench.ncu_facts()
+    # the committed ncu summary belongs to the committed kernels (bench.py refuses it otherwise and prints null fields)
+    assert facts is not None and facts["source_sha"] == h, "profiles/ncu_r2_summary.json is stale: re-capture with tools/ncu_ab.sh + tools/ncu_json.py"
