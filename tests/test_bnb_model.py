@@ -85,3 +85,22 @@ def test_lower_bound_is_monotone_in_floating_point():
         ex = ((x + c_acc) + c_ref) + cp
         assert lb <= ex
         assert (0.0 + c_acc) == c_acc
+
+
+def test_settled_column_shortcut():
+    """S-L kernel, columns whose work-list vote is empty: the row's minimum is its first-evaluated candidate k0 (the first
+    minimum of the lower bounds), exact - no final scan.  With ties everywhere: whenever no other candidate has
+    lb <= exact[k0], (exact[k0], k0) is what the full sweep returns."""
+    rng = np.random.default_rng(5)
+    settled = 0
+    for trial in range(20000):
+        n = int(rng.integers(1, 17))
+        lb = rng.integers(0, 12, n).astype(float)
+        exact = lb + rng.integers(0, 6, n).astype(float) * (rng.random(n) < 0.5)
+        _, k0 = full_sweep(lb)
+        ub = exact[k0]
+        if any(lb[k] <= ub for k in range(n) if k != k0):
+            continue                                            # the kernel builds a work list and re-scans the row
+        settled += 1
+        assert full_sweep(exact) == (ub, k0), (trial, lb, exact)
+    assert settled > 2000
